@@ -1,0 +1,591 @@
+/* TEST INFRASTRUCTURE ONLY (oracle). Not part of the shipped product path.
+ * See gpis_oracle.h for scope, pinning status and who may call this.
+ *
+ * Arithmetic conventions (REAL=float build): storage and linear algebra are fp32; the
+ * spots where the reference's unqualified exp()/sqrt()/double literals promote to double
+ *  are reproduced with explicit casts. Linear-algebra operation order is
+ * this file's own (row-oriented Cholesky-Banachiewicz, sequential sums): Eigen's order is
+ * not reproducible without its sources and is absorbed by the stated tolerances.
+ */
+#include "gpis_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+int gpo_real_bytes(void) { return (int)sizeof(real); }
+
+/* ------------------------------------------------------------------ a1: covFnc.cpp:29-33 */
+static real kf(real r, real a) { return (real)((1.0 + (double)(a * r)) * exp((double)(-a * r))); }
+static real kf1(real r, real dx, real a) { return (real)((double)(a * a * dx) * exp((double)(-a * r))); }
+static real kf2(real r, real dx1, real dx2, real delta, real a) {
+    return (real)((double)(a * a * (delta - a * dx1 * dx2 / r)) * exp((double)(-a * r)));
+}
+static real sqrt_real(real v) { return sizeof(real) == 4 ? (real)sqrtf((float)v) : (real)sqrt((double)v); }
+/* (x1.col(k)-x2.col(j)).norm(): sequential sum of squares, then sqrt in the scalar type */
+static real dist(const real* a, const real* b, int dim) {
+    real s = 0;
+    for (int c = 0; c < dim; ++c) { real d = a[c] - b[c]; s += d * d; }
+    return sqrt_real(s);
+}
+
+/* ------------------------------------------------------------------ a2: train covariance
+ * covFnc.cpp:142-256 (3D), 317-402 (2D). gradidx[k] = compacted index or -1
+ * (covFnc.cpp:151-161). K is n x n row-major, fully (symmetrically) filled. */
+static void matern_train_core(int dim, const real* x, const int* gradidx, int N, int ng, real scale,
+                              const real* sigx, const real* siggrad, real* K) {
+    const int n = N + dim * ng;
+    const real a = (real)(sqrt(3.0) / (double)scale); /* covFnc.cpp:147 */
+    const real a2 = a * a;
+    memset(K, 0, sizeof(real) * (size_t)n * n);
+#define KK(i, j) K[(size_t)(i) * n + (j)]
+    for (int k = 0; k < N; ++k) {
+        const int gk = gradidx[k];
+        for (int j = k; j < N; ++j) {
+            if (k == j) {
+                KK(k, k) = (real)(1.0 + (double)sigx[k]); /* :173 */
+                if (gk >= 0) {
+                    for (int c = 0; c < dim; ++c) {
+                        const int kc = N + c * ng + gk;
+                        if (dim == 2 && c == 0) /* 2D quirk, covFnc.cpp:352 */
+                            KK(kc, kc) = (real)((double)a2 + sqrt((double)(sigx[k] * siggrad[k])));
+                        else
+                            KK(kc, kc) = a2 + siggrad[k]; /* :182,186,190 / :355 */
+                    }
+                }
+                continue;
+            }
+            const real* xk = x + (size_t)k * dim;
+            const real* xj = x + (size_t)j * dim;
+            const real r = dist(xk, xj, dim);
+            const int gj = gradidx[j];
+            KK(k, j) = KK(j, k) = kf(r, a); /* :194-195 */
+            if (gk >= 0) {
+                for (int c = 0; c < dim; ++c) { /* :198-203 */
+                    const int kc = N + c * ng + gk;
+                    const real v = -kf1(r, xk[c] - xj[c], a);
+                    KK(kc, j) = KK(j, kc) = v;
+                }
+                if (gj >= 0) {
+                    for (int c = 0; c < dim; ++c) { /* :210-215: K(k,jind) = -K(j,kind) */
+                        const int kc = N + c * ng + gk, jc = N + c * ng + gj;
+                        const real v = -KK(j, kc);
+                        KK(k, jc) = KK(jc, k) = v;
+                    }
+                    for (int c = 0; c < dim; ++c) /* :217-237, upper computed, lower mirrored */
+                        for (int e = c; e < dim; ++e) {
+                            const int kc = N + c * ng + gk, ke = N + e * ng + gk;
+                            const int jc = N + c * ng + gj, je = N + e * ng + gj;
+                            const real v = kf2(r, xk[c] - xj[c], xk[e] - xj[e], c == e ? (real)1 : (real)0, a);
+                            KK(kc, je) = KK(je, kc) = v;
+                            if (e != c) KK(ke, jc) = KK(jc, ke) = v;
+                        }
+                }
+            } else if (gj >= 0) { /* :239-249 */
+                for (int c = 0; c < dim; ++c) {
+                    const int jc = N + c * ng + gj;
+                    const real v = kf1(r, xk[c] - xj[c], a);
+                    KK(k, jc) = KK(jc, k) = v;
+                }
+            }
+        }
+    }
+#undef KK
+}
+
+int gpo_matern_train(int dim, const float* x, const float* gradflag, int N, float scale, const float* sigx,
+                     const float* siggrad, real* K) {
+    int* gi = (int*)malloc(sizeof(int) * (N > 0 ? N : 1));
+    real* xr = (real*)malloc(sizeof(real) * (size_t)(N > 0 ? N : 1) * dim);
+    real* sx = (real*)malloc(sizeof(real) * (N > 0 ? N : 1));
+    real* sg = (real*)malloc(sizeof(real) * (N > 0 ? N : 1));
+    int ng = 0;
+    for (int k = 0; k < N; ++k) {
+        gi[k] = gradflag[k] > 0.5f ? ng++ : -1;
+        sx[k] = sigx[k]; sg[k] = siggrad[k];
+        for (int c = 0; c < dim; ++c) xr[(size_t)k * dim + c] = x[(size_t)k * dim + c];
+    }
+    if (K) matern_train_core(dim, xr, gi, N, ng, (real)scale, sx, sg, K);
+    free(gi); free(xr); free(sx); free(sg);
+    return N + dim * ng;
+}
+
+/* ------------------------------------------------------------------ a3: test covariance
+ * covFnc.cpp:258-314 (3D), 404-450 (2D), m = 1. Ks is n x (1+dim) row-major. */
+int gpo_matern_test(int dim, const real* x, const int* gradidx, int N, int ng, const real* xt, real scale,
+                    real* Ks) {
+    const int n = N + dim * ng, w = 1 + dim;
+    const real a = (real)(sqrt(3.0) / (double)scale);
+    memset(Ks, 0, sizeof(real) * (size_t)n * w);
+    for (int k = 0; k < N; ++k) {
+        const real* xk = x + (size_t)k * dim;
+        const real r = dist(xk, xt, dim);
+        real* row = Ks + (size_t)k * w;
+        row[0] = kf(r, a);
+        for (int c = 0; c < dim; ++c) row[1 + c] = kf1(r, xk[c] - xt[c], a);
+        const int gk = gradidx[k];
+        if (gk >= 0) {
+            for (int c = 0; c < dim; ++c) {
+                real* rc = Ks + (size_t)(N + c * ng + gk) * w;
+                rc[0] = -row[1 + c];
+                for (int e = 0; e < dim; ++e) {
+                    /* the reference evaluates the upper triangle and copies it down */
+                    const int c0 = c < e ? c : e, e0 = c < e ? e : c;
+                    rc[1 + e] = kf2(r, xk[c0] - xt[c0], xk[e0] - xt[e0], c == e ? (real)1 : (real)0, a);
+                }
+            }
+        }
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ dense LA helpers */
+/* Row-oriented Cholesky (lower, row-major, in place on the lower triangle). Returns the
+ * number of non-positive pivots (the reference never checks, OnGPIS.cpp:139). */
+static int chol_lower(real* A, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+        real* ai = A + (size_t)i * n;
+        for (int j = 0; j <= i; ++j) {
+            const real* aj = A + (size_t)j * n;
+            real s = ai[j];
+            for (int k = 0; k < j; ++k) s -= ai[k] * aj[k];
+            if (j < i) ai[j] = s / aj[j];
+            else {
+                if (!(s > 0)) ++bad;
+                ai[i] = sqrt_real(s);
+            }
+        }
+        for (int j = i + 1; j < n; ++j) ai[j] = 0;
+    }
+    return bad;
+}
+/* L z = b, nrhs columns stored row-major b[n][nrhs] */
+static void fwd_solve(const real* L, int n, real* b, int nrhs) {
+    for (int i = 0; i < n; ++i) {
+        const real* li = L + (size_t)i * n;
+        for (int c = 0; c < nrhs; ++c) {
+            real s = b[(size_t)i * nrhs + c];
+            for (int k = 0; k < i; ++k) s -= li[k] * b[(size_t)k * nrhs + c];
+            b[(size_t)i * nrhs + c] = s / li[i];
+        }
+    }
+}
+/* L^T a = z */
+static void bwd_solve(const real* L, int n, real* b) {
+    for (int i = n - 1; i >= 0; --i) {
+        real s = b[i];
+        for (int k = i + 1; k < n; ++k) s -= L[(size_t)k * n + i] * b[k];
+        b[i] = s / L[(size_t)i * n + i];
+    }
+}
+
+/* ------------------------------------------------------------------ a4: OnGPIS::train */
+struct gpo_gp {
+    int dim, N, ng, n, bad;
+    real scale;
+    real three_over_scale;
+    real* x;      /* N x dim */
+    int* gradidx; /* N */
+    real* alpha;  /* n */
+    real* L;      /* n x n row-major */
+};
+
+gpo_gp* gpo_gp_train(int dim, const float* samples, int N, float scale, float noise) {
+    (void)noise; /* "currently noise param is not effective" (OnGPIS.h:45-46) */
+    if (N <= 0) return NULL; /* OnGPIS.cpp:40,97: stays untrained */
+    const int w = 2 * dim + 3;
+    gpo_gp* g = (gpo_gp*)calloc(1, sizeof(gpo_gp));
+    g->dim = dim; g->N = N; g->scale = (real)scale;
+    g->three_over_scale = (real)(3.0 / (double)((real)scale * (real)scale)); /* OnGPIS.h:58 */
+    g->x = (real*)malloc(sizeof(real) * (size_t)N * dim);
+    g->gradidx = (int*)malloc(sizeof(int) * N);
+    real* sigx = (real*)malloc(sizeof(real) * N);
+    real* sigg = (real*)malloc(sizeof(real) * N);
+    real* f = (real*)malloc(sizeof(real) * N);
+    real* gv = (real*)malloc(sizeof(real) * (size_t)N * dim);
+    int ng = 0;
+    for (int k = 0; k < N; ++k) {
+        const float* s = samples + (size_t)k * w;
+        for (int c = 0; c < dim; ++c) g->x[(size_t)k * dim + c] = s[c];
+        f[k] = s[2 * dim];
+        sigx[k] = s[2 * dim + 1];
+        sigg[k] = s[2 * dim + 2];
+        int allsmall = 1;
+        for (int c = 0; c < dim; ++c)
+            if (!(fabs((double)s[dim + c]) < 1e-6)) allsmall = 0;
+        /* OnGPIS.cpp:63-66 / 122-125: float siggrad compared with the double literal */
+        if ((double)s[2 * dim + 2] > 0.1001 || allsmall) {
+            g->gradidx[k] = -1;
+            sigx[k] = 2.0;
+        } else {
+            for (int c = 0; c < dim; ++c) gv[(size_t)ng * dim + c] = s[dim + c];
+            g->gradidx[k] = ng++;
+        }
+    }
+    g->ng = ng;
+    const int n = g->n = N + dim * ng;
+    g->alpha = (real*)malloc(sizeof(real) * n);
+    g->L = (real*)malloc(sizeof(real) * (size_t)n * n);
+    /* y = [f; gx(valid); gy(valid); gz(valid)]  (OnGPIS.cpp:75-76, 135-136) */
+    for (int k = 0; k < N; ++k) g->alpha[k] = f[k];
+    for (int c = 0; c < dim; ++c)
+        for (int q = 0; q < ng; ++q) g->alpha[N + c * ng + q] = gv[(size_t)q * dim + c];
+    matern_train_core(dim, g->x, g->gradidx, N, ng, g->scale, sigx, sigg, g->L);
+    g->bad = chol_lower(g->L, n);              /* :139 */
+    fwd_solve(g->L, n, g->alpha, 1);           /* :141-142 */
+    bwd_solve(g->L, n, g->alpha);              /* :143 */
+    free(sigx); free(sigg); free(f); free(gv);
+    return g;
+}
+void gpo_gp_free(gpo_gp* g) {
+    if (!g) return;
+    free(g->x); free(g->gradidx); free(g->alpha); free(g->L); free(g);
+}
+int gpo_gp_n(const gpo_gp* g) { return g ? g->n : 0; }
+int gpo_gp_ng(const gpo_gp* g) { return g ? g->ng : 0; }
+int gpo_gp_chol_fail(const gpo_gp* g) { return g ? g->bad : 0; }
+void gpo_gp_get(const gpo_gp* g, real* alpha, real* L, float* gradflag) {
+    if (alpha) memcpy(alpha, g->alpha, sizeof(real) * g->n);
+    if (L) memcpy(L, g->L, sizeof(real) * (size_t)g->n * g->n);
+    if (gradflag)
+        for (int k = 0; k < g->N; ++k) gradflag[k] = g->gradidx[k] >= 0 ? 1.f : 0.f;
+}
+
+/* ------------------------------------------------------------------ a5: testSinglePoint
+ * OnGPIS.cpp:177-216 (3D) / 218-239 (2D). out = [f, grad(dim), var(1+dim)] written in place. */
+static void gp_test_point(const gpo_gp* g, const real* xt, real* out) {
+    const int n = g->n, dim = g->dim, w = 1 + dim;
+    real* Ks = (real*)malloc(sizeof(real) * (size_t)n * w);
+    gpo_matern_test(dim, g->x, g->gradidx, g->N, g->ng, xt, g->scale, Ks);
+    for (int c = 0; c < w; ++c) { /* K^T alpha, :187 */
+        real s = 0;
+        for (int i = 0; i < n; ++i) s += Ks[(size_t)i * w + c] * g->alpha[i];
+        out[c] = s;
+    }
+    fwd_solve(g->L, n, Ks, w); /* :199 */
+    for (int c = 0; c < w; ++c) {
+        real s = 0;
+        for (int i = 0; i < n; ++i) { real v = Ks[(size_t)i * w + c]; s += v * v; }
+        /* priors: :203-212 (3D: 1.001, 3/l^2+0.001), :235-237 (2D: 1.01, 3/l^2+0.1) */
+        double prior;
+        if (dim == 3) prior = c == 0 ? 1.001 : (double)g->three_over_scale + 0.001;
+        else prior = c == 0 ? 1.01 : (double)g->three_over_scale + 0.1;
+        out[w + c] = (real)(prior - (double)s);
+    }
+    free(Ks);
+}
+void gpo_gp_test(const gpo_gp* g, const real* x, int m, real* res) {
+    if (!g) return; /* untrained: outputs untouched (OnGPIS.cpp:179-180) */
+    const int w = 2 * (1 + g->dim);
+    for (int i = 0; i < m; ++i) gp_test_point(g, x + (size_t)i * g->dim, res + (size_t)i * w);
+}
+
+/* ------------------------------------------------------------------ a13 + a14: map query */
+struct gpo_map {
+    int dim, nc;
+    float* centres; /* nc x dim */
+    float half, search_half;
+    real var_thre, noise;
+    gpo_gp** gps;
+};
+gpo_map* gpo_map_create(int dim, int nclusters, const float* centres, float cluster_half, gpo_gp* const* gps,
+                        float search_half, float var_thre, float noise) {
+    gpo_map* m = (gpo_map*)calloc(1, sizeof(gpo_map));
+    m->dim = dim; m->nc = nclusters; m->half = cluster_half; m->search_half = search_half;
+    m->var_thre = (real)var_thre; m->noise = (real)noise;
+    m->centres = (float*)malloc(sizeof(float) * (size_t)(nclusters > 0 ? nclusters : 1) * dim);
+    memcpy(m->centres, centres, sizeof(float) * (size_t)nclusters * dim);
+    m->gps = (gpo_gp**)malloc(sizeof(gpo_gp*) * (nclusters > 0 ? nclusters : 1));
+    memcpy(m->gps, gps, sizeof(gpo_gp*) * nclusters);
+    return m;
+}
+void gpo_map_free(gpo_map* m) {
+    if (!m) return;
+    free(m->centres); free(m->gps); free(m);
+}
+
+/* One query: GPisMap3.cpp:803-900 / GPisMap.cpp:673-761. Geometry is always fp32 (it decides
+ * the neighbour set and must be bit-exact): AABB c-l / c+l and x-h / x+h in float,
+ * inclusive overlap (octree.h:128-135), sqdist as dx*dx+dy*dy+dz*dz (octree.cpp:24-31). */
+static void map_test_point(const gpo_map* m, const float* x, real* res, int* chosen, int* tie, int* idx,
+                           float* sq) {
+    const int dim = m->dim, w = 1 + dim;
+    int nc = 0;
+    float qlo[3], qhi[3];
+    for (int c = 0; c < dim; ++c) { qlo[c] = x[c] - m->search_half; qhi[c] = x[c] + m->search_half; }
+    for (int i = 0; i < m->nc; ++i) {
+        const float* ct = m->centres + (size_t)i * dim;
+        int hit = 1;
+        for (int c = 0; c < dim; ++c) {
+            const float lo = ct[c] - m->half, hi = ct[c] + m->half;
+            if (qhi[c] < lo || qlo[c] > hi) { hit = 0; break; }
+        }
+        if (!hit) continue;
+        float s = 0.f;
+        for (int c = 0; c < dim; ++c) { float d = ct[c] - x[c]; s = c == 0 ? d * d : s + d * d; }
+        idx[nc] = i; sq[nc] = s; ++nc;
+    }
+    /* stable insertion sort by distance == std::sort for <= 16 elements; for more the
+     * reference's introsort may order exact ties differently: flagged. */
+    for (int i = 1; i < nc; ++i) {
+        int ii = idx[i]; float si = sq[i]; int j = i - 1;
+        while (j >= 0 && sq[j] > si) { idx[j + 1] = idx[j]; sq[j + 1] = sq[j]; --j; }
+        idx[j + 1] = ii; sq[j + 1] = si;
+    }
+    const int numc = nc > 3 ? 3 : nc;
+    if (chosen) {
+        chosen[0] = nc;
+        for (int k = 0; k < 3; ++k) chosen[1 + k] = k < numc ? idx[k] : -1;
+    }
+    if (tie) {
+        *tie = 0;
+        for (int k = 0; k < numc && k + 1 < nc; ++k)
+            if (sq[k] == sq[k + 1]) *tie = 1;
+    }
+    res[w] = (real)(1.0 + (double)(float)m->noise); /* :816 */
+    if (nc == 0) return;
+    const real xt[3] = {x[0], x[1], dim == 3 ? x[2] : 0};
+    if (nc == 1) { /* :818-823 */
+        if (m->gps[idx[0]]) gp_test_point(m->gps[idx[0]], xt, res);
+        return;
+    }
+    if (m->gps[idx[0]]) gp_test_point(m->gps[idx[0]], xt, res); /* :832-835 */
+    if (!(res[w] > m->var_thre)) return;                          /* :837 */
+    real cand[3][8];
+    for (int c = 0; c < 2 * w; ++c) cand[0][c] = res[c];
+    for (int k = 1; k < numc; ++k) { /* :847-854; a NULL gp there is UB in the reference */
+        for (int c = 0; c < 2 * w; ++c) cand[k][c] = res[c];
+        cand[k][w] = (real)1e30;
+        if (m->gps[idx[k]]) gp_test_point(m->gps[idx[k]], xt, cand[k]);
+    }
+    int ord[3] = {0, 1, 2};
+    for (int i = 1; i < numc; ++i) { /* :864-867: sort the <=3 by var_f (stable) */
+        int oi = ord[i]; int j = i - 1;
+        while (j >= 0 && cand[ord[j]][w] > cand[oi][w]) { ord[j + 1] = ord[j]; --j; }
+        ord[j + 1] = oi;
+    }
+    const real* A = cand[ord[0]];
+    if (A[w] < m->var_thre) { /* :869-880 */
+        for (int c = 0; c < 2 * w; ++c) res[c] = A[c];
+    } else { /* :881-895 */
+        const real* B = cand[ord[1]];
+        const real w1 = A[w] - m->var_thre, w2 = B[w] - m->var_thre, w12 = w1 + w2;
+        for (int c = 0; c < 2 * w; ++c) res[c] = (w2 * A[c] + w1 * B[c]) / w12;
+    }
+}
+void gpo_map_test(const gpo_map* m, const float* x, int n, real* res, int* chosen, int* tie) {
+    int* idx = (int*)malloc(sizeof(int) * (m->nc > 0 ? m->nc : 1));
+    float* sq = (float*)malloc(sizeof(float) * (m->nc > 0 ? m->nc : 1));
+    const int w = 2 * (1 + m->dim);
+    for (int i = 0; i < n; ++i)
+        map_test_point(m, x + (size_t)i * m->dim, res + (size_t)i * w, chosen ? chosen + 4 * i : NULL,
+                       tie ? tie + i : NULL, idx, sq);
+    free(idx); free(sq);
+}
+
+/* ------------------------------------------------------------------ a7/a8: OU kernel, GPou */
+typedef struct {
+    int n, d;
+    real* x;     /* n x d */
+    real* alpha; /* n */
+    real* L;     /* n x n */
+} gpou;
+#define OBS_SCALE 0.5f /* params.h:97 */
+#define OBS_NOISE 0.01f /* params.h:98 */
+
+/* ObsGP.cpp:32-48 + covFnc.cpp:47-68 */
+static gpou* gpou_train(const real* x, const real* f, int n, int d) {
+    gpou* g = (gpou*)calloc(1, sizeof(gpou));
+    g->n = n; g->d = d;
+    g->x = (real*)malloc(sizeof(real) * (size_t)n * d);
+    memcpy(g->x, x, sizeof(real) * (size_t)n * d);
+    g->alpha = (real*)malloc(sizeof(real) * n);
+    memcpy(g->alpha, f, sizeof(real) * n);
+    g->L = (real*)malloc(sizeof(real) * (size_t)n * n);
+    const real a = (real)1 / (real)OBS_SCALE;
+    for (int k = 0; k < n; ++k)
+        for (int j = k; j < n; ++j) {
+            real v;
+            if (k == j) v = (real)(1.0 + (double)(real)OBS_NOISE);
+            else v = (real)exp((double)(-a * dist(x + (size_t)k * d, x + (size_t)j * d, d)));
+            g->L[(size_t)k * n + j] = g->L[(size_t)j * n + k] = v;
+        }
+    chol_lower(g->L, n);
+    fwd_solve(g->L, n, g->alpha, 1);
+    bwd_solve(g->L, n, g->alpha);
+    return g;
+}
+static void gpou_free(gpou* g) {
+    if (!g) return;
+    free(g->x); free(g->alpha); free(g->L); free(g);
+}
+/* ObsGP.cpp:50-62 + covFnc.cpp:93-109, single test point */
+static void gpou_test(const gpou* g, const real* xt, real* f, real* var) {
+    const int n = g->n;
+    real* k = (real*)malloc(sizeof(real) * n);
+    const real a = (real)1 / (real)OBS_SCALE;
+    for (int i = 0; i < n; ++i) k[i] = (real)exp((double)(-a * dist(g->x + (size_t)i * g->d, xt, g->d)));
+    real s = 0;
+    for (int i = 0; i < n; ++i) s += k[i] * g->alpha[i];
+    *f = s;
+    fwd_solve(g->L, n, k, 1);
+    s = 0;
+    for (int i = 0; i < n; ++i) s += k[i] * k[i];
+    *var = ((real)1 + (real)OBS_NOISE) - s;
+    free(k);
+}
+
+/* ------------------------------------------------------------------ a9/a10: partitioned GPs */
+struct gpo_obs {
+    int d;          /* 1 or 2 */
+    int ng0, ng1;   /* tile grid (ng1 = 1 in 1-D) */
+    int nb0, nb1;   /* boundary counts */
+    float* b0;      /* Val_i / range */
+    float* b1;      /* Val_j */
+    gpou** gps;
+    int ngps;
+    float margin;
+};
+#define OBS_GROUP2 5    /* params.h:108-110 */
+#define OBS_OVERLAP2 3
+#define OBS_MARGIN2 0.005f
+#define OBS_GROUP1 20   /* params.h:101-103 */
+#define OBS_OVERLAP1 6
+#define OBS_MARGIN1 0.0175f
+
+/* ObsGP.cpp:204-265 (partition) + 280-329 (training of tiles with >= 1 valid pixel) */
+gpo_obs* gpo_obs2d_train(const float* vu, const float* zinv, int ni, int nj) {
+    if (ni <= 0 || nj <= 0 || !vu) return NULL;
+    gpo_obs* o = (gpo_obs*)calloc(1, sizeof(gpo_obs));
+    o->d = 2; o->margin = OBS_MARGIN2;
+    const int g = OBS_GROUP2, ov = OBS_OVERLAP2;
+    o->ng0 = (ni - ov) / g + 1;
+    o->ng1 = (nj - ov) / g + 1;
+    o->b0 = (float*)malloc(sizeof(float) * (o->ng0 + 1));
+    o->b1 = (float*)malloc(sizeof(float) * (o->ng1 + 1));
+    int* i0 = (int*)malloc(sizeof(int) * o->ng0), *i1 = (int*)malloc(sizeof(int) * o->ng0);
+    int* j0 = (int*)malloc(sizeof(int) * o->ng1), *j1 = (int*)malloc(sizeof(int) * o->ng1);
+    o->b0[0] = vu[0];
+    for (int n = 0; n < o->ng0; ++n) {
+        i0[n] = n * g;
+        i1[n] = i0[n] + g + ov - 1;
+        if (n < o->ng0 - 1) o->b0[n + 1] = vu[2 * (i1[n] - ov / 2)];
+        else { i1[n] = ni - 1; o->b0[n + 1] = vu[2 * i1[n]]; }
+    }
+    o->b1[0] = vu[1];
+    for (int m = 0; m < o->ng1; ++m) {
+        j0[m] = m * g;
+        j1[m] = j0[m] + g + ov - 1;
+        if (m < o->ng1 - 1) o->b1[m + 1] = vu[2 * (j1[m] - ov / 2) * ni + 1];
+        else { j1[m] = nj - 1; o->b1[m + 1] = vu[2 * j1[m] * ni + 1]; }
+    }
+    o->nb0 = o->ng0 + 1; o->nb1 = o->ng1 + 1;
+    o->ngps = o->ng0 * o->ng1;
+    o->gps = (gpou**)calloc(o->ngps > 0 ? o->ngps : 1, sizeof(gpou*));
+    const int cap = (g + ov + 8) * (g + ov + 8) + ni + nj;
+    real* xs = (real*)malloc(sizeof(real) * 2 * (size_t)cap * 4);
+    real* fs = (real*)malloc(sizeof(real) * (size_t)cap * 4);
+    for (int m = 0; m < o->ng1; ++m)
+        for (int n = 0; n < o->ng0; ++n) {
+            int cnt = 0;
+            for (int j = j0[m]; j <= j1[m]; ++j)
+                for (int i = i0[n]; i <= i1[n]; ++i) {
+                    const int ind = j * ni + i;
+                    if (zinv[ind] > 0) {
+                        xs[2 * cnt] = vu[2 * ind]; xs[2 * cnt + 1] = vu[2 * ind + 1];
+                        fs[cnt] = zinv[ind]; ++cnt;
+                    }
+                }
+            if (cnt >= 1) o->gps[m * o->ng0 + n] = gpou_train(xs, fs, cnt, 2);
+        }
+    free(xs); free(fs); free(i0); free(i1); free(j0); free(j1);
+    return o;
+}
+
+/* ObsGP.cpp:85-143 */
+gpo_obs* gpo_obs1d_train(const float* theta, const float* f, int N) {
+    if (N <= 0 || !theta) return NULL;
+    gpo_obs* o = (gpo_obs*)calloc(1, sizeof(gpo_obs));
+    o->d = 1; o->margin = OBS_MARGIN1;
+    const int g = OBS_GROUP1, ov = OBS_OVERLAP1;
+    const int nGroup = N / g + 1;
+    o->ng0 = nGroup; o->ng1 = 1;
+    o->b0 = (float*)malloc(sizeof(float) * (nGroup + 2));
+    o->gps = (gpou**)calloc(nGroup + 1, sizeof(gpou*));
+    real* xs = (real*)malloc(sizeof(real) * (size_t)(N + 1));
+    real* fs = (real*)malloc(sizeof(real) * (size_t)(N + 1));
+    for (int i = 0; i < N; ++i) { xs[i] = theta[i]; fs[i] = f[i]; }
+    int nb = 0, ngp = 0;
+    o->b0[nb++] = theta[0];
+    for (int n = 0; n < nGroup - 1; ++n) {
+        if (n < nGroup - 2) {
+            const int a = n * g, b = a + g + ov;
+            o->b0[nb++] = theta[b - ov / 2];
+            o->gps[ngp++] = gpou_train(xs + a, fs + a, g + ov, 1);
+        } else { /* the last two groups split the remainder in half (:114-136) */
+            int a = n * g;
+            int b = a + (N - a) / 2 + ov;
+            o->b0[nb++] = theta[b - ov / 2];
+            o->gps[ngp++] = gpou_train(xs + a, fs + a, b - a + 1, 1);
+            ++n;
+            a = a + (N - a) / 2;
+            b = N - 1;
+            o->b0[nb++] = theta[b];
+            o->gps[ngp++] = gpou_train(xs + a, fs + a, b - a + 1, 1);
+        }
+    }
+    o->nb0 = nb; o->nb1 = 0; o->ngps = ngp;
+    free(xs); free(fs);
+    return o;
+}
+void gpo_obs_free(gpo_obs* o) {
+    if (!o) return;
+    for (int i = 0; i < o->ngps; ++i) gpou_free(o->gps[i]);
+    free(o->gps); free(o->b0); free(o->b1); free(o);
+}
+int gpo_obs_ntiles(const gpo_obs* o) { return o ? o->ngps : 0; }
+void gpo_obs_tile_counts(const gpo_obs* o, int* counts) {
+    for (int i = 0; i < o->ngps; ++i) counts[i] = o->gps[i] ? o->gps[i]->n : 0;
+}
+int gpo_obs_bounds(const gpo_obs* o, float* bi, float* bj) {
+    if (bi) memcpy(bi, o->b0, sizeof(float) * o->nb0);
+    if (bj && o->nb1) memcpy(bj, o->b1, sizeof(float) * o->nb1);
+    return o->nb0 * 65536 + o->nb1;
+}
+
+void gpo_obs_test(const gpo_obs* o, const float* xt, int m, real* val, real* var) {
+    if (!o) return; /* untrained: outputs untouched (ObsGP.cpp:147-149, 412-414) */
+    for (int k = 0; k < m; ++k) {
+        var[k] = (real)1e6;
+        if (o->d == 2) { /* ObsGP.cpp:359-406 */
+            const float x0 = xt[2 * k], x1 = xt[2 * k + 1];
+            if (x0 < o->b0[0] + o->margin) continue;
+            if (x0 > o->b0[o->nb0 - 1] - o->margin) continue;
+            if (x1 < o->b1[0] + o->margin) continue;
+            if (x1 > o->b1[o->nb1 - 1] - o->margin) continue;
+            int n = 0, mm = 0;
+            for (int i = 1; i < o->nb0; ++i, ++n)
+                if (x0 < o->b0[i]) break;
+            for (int i = 1; i < o->nb1; ++i, ++mm)
+                if (x1 < o->b1[i]) break;
+            const int ind = mm * o->ng0 + n;
+            if (ind < o->ngps && o->gps[ind]) {
+                const real p[2] = {x0, x1};
+                gpou_test(o->gps[ind], p, &val[k], &var[k]);
+            }
+        } else { /* ObsGP.cpp:154-185 */
+            const float x0 = xt[k];
+            const float liml = o->b0[0] + o->margin, limr = o->b0[o->nb0 - 1] - o->margin;
+            if (x0 < liml || x0 > limr) continue;
+            for (int j = 0; j + 1 < o->nb0; ++j)
+                if (x0 > o->b0[j] && x0 < o->b0[j + 1]) {
+                    if (j < o->ngps && o->gps[j]) {
+                        const real p[1] = {x0};
+                        gpou_test(o->gps[j], p, &val[k], &var[k]);
+                    }
+                    break;
+                }
+        }
+    }
+}
