@@ -1,0 +1,996 @@
+// libgpis_b200.so — C ABI (include/gpis_b200.h) over the hand-written sm_100a kernels.
+// Host side of the boundary: context, device arena for leaf records, host mirror of the leaf
+// table for memory management, parameter derivation with the reference's exact mixed
+// float/double expressions. There is no CPU compute path in this library.
+#include "../../include/gpis_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "leaf_train.cuh"
+#include "obs_gp.cuh"
+#include "query.cuh"
+#include "query_v2.cuh"
+
+using namespace gpis;
+
+// ------------------------------------------------------------------ K3: table maintenance kernels
+namespace gpis {
+
+struct SlotUpdate {
+    uint64_t key;
+    uint64_t rec;
+    int32_t slot;
+    int32_t live;     // 1 = upsert, 0 = erase
+    int32_t cell[3];
+    float centre[3];
+    float lo[3], hi[3];
+    int32_t meta[4];  // N, ng, n, nb
+};
+
+__global__ void k_table_apply(LeafTable T, const SlotUpdate* __restrict__ ups, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SlotUpdate u = ups[i];
+    if (u.live) {
+        // slot arrays first, then publish the key
+        T.centre[u.slot] = make_float4(u.centre[0], u.centre[1], u.centre[2], 0.f);
+        T.lo[u.slot] = make_float4(u.lo[0], u.lo[1], u.lo[2], 0.f);
+        T.hi[u.slot] = make_float4(u.hi[0], u.hi[1], u.hi[2], 0.f);
+        T.cell[u.slot] = make_int4(u.cell[0], u.cell[1], u.cell[2], 1);
+        T.rec[u.slot] = u.rec;
+        T.meta[u.slot] = make_int4(u.meta[0], u.meta[1], u.meta[2], u.meta[3]);
+        uint32_t h = hash_key(u.key) & T.cap_mask;
+        for (uint32_t probe = 0; probe <= T.cap_mask; ++probe) {
+            const uint64_t prev = atomicCAS(reinterpret_cast<unsigned long long*>(T.keys + h),
+                                            (unsigned long long)GPIS_KEY_EMPTY, (unsigned long long)u.key);
+            if (prev == GPIS_KEY_EMPTY || prev == u.key) { T.vals[h] = u.slot; return; }
+            h = (h + 1) & T.cap_mask;
+        }
+    } else {
+        uint32_t h = hash_key(u.key) & T.cap_mask;
+        for (uint32_t probe = 0; probe <= T.cap_mask; ++probe) {
+            const uint64_t k = T.keys[h];
+            if (k == u.key) { T.keys[h] = GPIS_KEY_TOMB; T.vals[h] = -1; break; }
+            if (k == GPIS_KEY_EMPTY) break;
+            h = (h + 1) & T.cap_mask;
+        }
+        T.rec[u.slot] = 0ull;
+        T.cell[u.slot] = make_int4(0, 0, 0, 0);
+    }
+}
+
+// Re-insert every live slot into a fresh key array (after growth or too many tombstones).
+__global__ void k_table_rebuild(LeafTable T, int nslots) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const int4 c = T.cell[s];
+    if (c.w == 0) return;
+    const uint64_t key = cell_key(c.x, c.y, c.z);
+    uint32_t h = hash_key(key) & T.cap_mask;
+    for (uint32_t probe = 0; probe <= T.cap_mask; ++probe) {
+        const uint64_t prev = atomicCAS(reinterpret_cast<unsigned long long*>(T.keys + h),
+                                        (unsigned long long)GPIS_KEY_EMPTY, (unsigned long long)key);
+        if (prev == GPIS_KEY_EMPTY) { T.vals[h] = s; return; }
+        h = (h + 1) & T.cap_mask;
+    }
+}
+
+// Unpack a dense lower-triangular L (row-major n x n) from the tile array, for gpis_leaf_get.
+__global__ void k_unpack_L(const float* __restrict__ tiles, int n, int nb, float* __restrict__ Ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n) return;
+    const int r = i / n, c = i % n;
+    float v = 0.f;
+    if (c <= r) {
+        const int bi = r >> 5, bj = c >> 5;
+        if (bi == bj) v = tiles[(size_t)tile_index(bi, bj, nb) * GPIS_TILE_ELEMS + (c & 31) * 32 + (r & 31)];
+        else {  // off-diagonal tiles hold G = L_ij inv(Ljj): L_ij = G Ljj
+            const float* G = tiles + (size_t)tile_index(bi, bj, nb) * GPIS_TILE_ELEMS;
+            const float* Ljj = tiles + (size_t)tile_index(bj, bj, nb) * GPIS_TILE_ELEMS;
+            for (int k = (c & 31); k < 32; ++k) v = fmaf(G[k * 32 + (r & 31)], Ljj[(c & 31) * 32 + k], v);
+        }
+    }
+    Ld[i] = v;
+}
+
+}  // namespace gpis
+
+// ------------------------------------------------------------------ context
+struct HostLeaf {
+    int slot;
+    uint64_t rec;      // device address, 0 = untrained
+    uint64_t rec_bytes;
+    int N, ng, n, nb;
+    int cell[3];
+    float centre[3];
+    float lo[3], hi[3];   // effective box (default: centre -/+ cluster_half)
+    bool box_set;
+};
+
+struct ArenaChunk { unsigned char* base; uint64_t size; };
+
+struct gpis_ctx {
+    gpis_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // leaf table
+    LeafTable T{};
+    uint32_t table_cap = 0;
+    int slot_cap = 0, slot_count = 0, tombs = 0;
+    std::vector<int> free_slots;
+    std::unordered_map<uint64_t, HostLeaf> leaves;
+    // arena
+    std::vector<ArenaChunk> chunks;
+    std::map<uint64_t, uint64_t> free_blocks;  // address -> size
+    uint64_t arena_used = 0, arena_reserved = 0;
+    // params
+    QueryParams qp{};
+    TrainParams tp{};
+    int max_nb = 1;
+    int max_N = 1;
+    // scratch
+    void* d_scratch = nullptr; uint64_t scratch_bytes = 0;       // generic upload buffer
+    void* d_scratch2 = nullptr; uint64_t scratch2_bytes = 0;
+    QueryWork W{}; int64_t work_cap = 0;
+    void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
+    int32_t* d_sort = nullptr; int64_t sort_cap = 0;
+    // obs gp
+    ObsTile* obs_tiles = nullptr; int obs_tile_cap = 0;
+    ObsTileDesc* obs_desc = nullptr;
+    float* obs_b0 = nullptr; float* obs_b1 = nullptr; int obs_b_cap = 0;
+    ObsParams op{}; bool obs_trained = false;
+    int obs_ni = -1, obs_nj = -1; bool obs_repartition = true;
+    std::vector<float> obs_hb0, obs_hb1; std::vector<ObsTileDesc> obs_hdesc;
+    // dirty export
+    std::vector<uint64_t> dirty_keys;
+    void* d_export = nullptr; uint64_t export_cap = 0;
+    gpis_stats st{};
+    int eval_version = 2;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return GPIS_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+static int ensure(gpis_ctx* ctx, void** p, uint64_t* cap, uint64_t need) {
+    if (*cap >= need) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    uint64_t sz = std::max<uint64_t>(need, 1 << 20);
+    sz = sz + sz / 4;
+    CK(cudaMalloc(p, sz));
+    *cap = sz;
+    return 0;
+}
+
+static uint64_t key_of(const gpis_ctx* ctx, const int32_t* cell) {
+    return cell_key(cell[0], cell[1], ctx->cfg.dim == 3 ? cell[2] : 0);
+}
+
+// ---- arena: first-fit free list over cudaMalloc'd chunks
+static int arena_alloc(gpis_ctx* ctx, uint64_t bytes, uint64_t* out) {
+    bytes = align_up(bytes, 256);
+    for (auto it = ctx->free_blocks.begin(); it != ctx->free_blocks.end(); ++it) {
+        if (it->second >= bytes) {
+            const uint64_t addr = it->first, sz = it->second;
+            ctx->free_blocks.erase(it);
+            if (sz > bytes) ctx->free_blocks[addr + bytes] = sz - bytes;
+            ctx->arena_used += bytes;
+            *out = addr;
+            return 0;
+        }
+    }
+    uint64_t csz = std::max<uint64_t>(ctx->cfg.arena_chunk_bytes, align_up(bytes, 1 << 20));
+    unsigned char* base = nullptr;
+    CK(cudaMalloc(&base, csz));
+    ctx->chunks.push_back({base, csz});
+    ctx->arena_reserved += csz;
+    ctx->free_blocks[(uint64_t)base] = csz;
+    return arena_alloc(ctx, bytes, out);
+}
+static void arena_free(gpis_ctx* ctx, uint64_t addr, uint64_t bytes) {
+    bytes = align_up(bytes, 256);
+    ctx->arena_used -= bytes;
+    auto it = ctx->free_blocks.emplace(addr, bytes).first;
+    // coalesce with the next / previous block when contiguous inside one chunk
+    auto nx = std::next(it);
+    if (nx != ctx->free_blocks.end() && it->first + it->second == nx->first) {
+        bool same = false;
+        for (auto& c : ctx->chunks) if (it->first >= (uint64_t)c.base && nx->first < (uint64_t)c.base + c.size) same = true;
+        if (same) { it->second += nx->second; ctx->free_blocks.erase(nx); }
+    }
+    if (it != ctx->free_blocks.begin()) {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first) {
+            bool same = false;
+            for (auto& c : ctx->chunks) if (pv->first >= (uint64_t)c.base && it->first < (uint64_t)c.base + c.size) same = true;
+            if (same) { pv->second += it->second; ctx->free_blocks.erase(it); }
+        }
+    }
+}
+
+// ---- table storage
+static int table_alloc(gpis_ctx* ctx, uint32_t cap, int slot_cap) {
+    LeafTable N{};
+    CK(cudaMalloc(&N.keys, sizeof(uint64_t) * cap));
+    CK(cudaMalloc(&N.vals, sizeof(int32_t) * cap));
+    CK(cudaMemsetAsync(N.keys, 0, sizeof(uint64_t) * cap, ctx->stream));
+    CK(cudaMemsetAsync(N.vals, 0xff, sizeof(int32_t) * cap, ctx->stream));
+    N.cap_mask = cap - 1;
+    CK(cudaMalloc(&N.centre, sizeof(float4) * slot_cap));
+    CK(cudaMalloc(&N.lo, sizeof(float4) * slot_cap));
+    CK(cudaMalloc(&N.hi, sizeof(float4) * slot_cap));
+    CK(cudaMalloc(&N.cell, sizeof(int4) * slot_cap));
+    CK(cudaMalloc(&N.rec, sizeof(uint64_t) * slot_cap));
+    CK(cudaMalloc(&N.meta, sizeof(int4) * slot_cap));
+    CK(cudaMemsetAsync(N.cell, 0, sizeof(int4) * slot_cap, ctx->stream));
+    CK(cudaMemsetAsync(N.rec, 0, sizeof(uint64_t) * slot_cap, ctx->stream));
+    if (ctx->T.keys) {
+        const int old = ctx->slot_cap;
+        CK(cudaMemcpyAsync(N.centre, ctx->T.centre, sizeof(float4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(N.lo, ctx->T.lo, sizeof(float4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(N.hi, ctx->T.hi, sizeof(float4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(N.cell, ctx->T.cell, sizeof(int4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(N.rec, ctx->T.rec, sizeof(uint64_t) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(N.meta, ctx->T.meta, sizeof(int4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (ctx->slot_count > 0) {
+            k_table_rebuild<<<(ctx->slot_count + 255) / 256, 256, 0, ctx->stream>>>(N, ctx->slot_count);
+            ctx->st.kernel_launches++;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->T.keys); cudaFree(ctx->T.vals); cudaFree(ctx->T.centre); cudaFree(ctx->T.cell);
+        cudaFree(ctx->T.rec); cudaFree(ctx->T.meta); cudaFree(ctx->T.lo); cudaFree(ctx->T.hi);
+    }
+    ctx->T = N;
+    ctx->table_cap = cap;
+    ctx->slot_cap = slot_cap;
+    ctx->tombs = 0;
+    return 0;
+}
+static int table_reserve(gpis_ctx* ctx, int extra) {
+    const int need_slots = ctx->slot_count + extra;
+    if (need_slots <= ctx->slot_cap && (uint64_t)(ctx->leaves.size() + ctx->tombs + extra) * 2 <= ctx->table_cap) return 0;
+    int sc = std::max(ctx->slot_cap, 1024);
+    while (sc < need_slots) sc *= 2;
+    uint32_t cap = std::max<uint32_t>(ctx->table_cap, 4096);
+    while ((uint64_t)(ctx->leaves.size() + extra) * 4 > cap) cap *= 2;
+    return table_alloc(ctx, cap, sc);
+}
+
+static void derive_params(gpis_ctx* ctx) {
+    const gpis_config& c = ctx->cfg;
+    QueryParams& q = ctx->qp;
+    q.dim = c.dim;
+    q.cluster_half = c.cluster_half;
+    q.search_half = c.search_half;
+    q.var_thre = c.var_thre;
+    q.var_preset = (float)(1.0 + (double)c.map_noise);                 // GPisMap3.cpp:816
+    q.a = (float)(std::sqrt(3.0) / (double)c.map_scale);               // covFnc.cpp:263
+    const float three_over_scale = (float)(3.0 / (double)(c.map_scale * c.map_scale));  // OnGPIS.h:58
+    if (c.dim == 3) { q.prior_f = 1.001f; q.prior_g = (double)three_over_scale + 0.001; }   // OnGPIS.cpp:203-212
+    else            { q.prior_f = 1.01f;  q.prior_g = (double)three_over_scale + 0.1; }     // OnGPIS.cpp:235-237
+    q.inv_pitch = 1.0 / (2.0 * (double)c.cluster_half);
+    q.root_min[0] = q.root_min[1] = q.root_min[2] = -(1 << 19);
+    q.levels = 20;
+    TrainParams& t = ctx->tp;
+    t.dim = c.dim;
+    t.scale = c.map_scale;
+    t.a = (float)(std::sqrt(3.0) / (double)c.map_scale);               // covFnc.cpp:147
+    t.a2 = t.a * t.a;
+    ObsParams& o = ctx->op;
+    o.a = 1 / c.obs_scale;                                             // covFnc.cpp:51
+    o.diag = (float)(1.0 + (double)c.obs_noise);                       // covFnc.cpp:57
+    o.var_prior = 1 + c.obs_noise;                                     // ObsGP.cpp:61
+}
+
+extern "C" {
+
+int gpis_config_default(gpis_config* cfg, int dim) {
+    if (!cfg || (dim != 2 && dim != 3)) return GPIS_ERR_ARG;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->dim = dim;
+    cfg->device = 0;
+    if (dim == 3) {
+        cfg->map_scale = 0.04f;                  // params.h:92
+        cfg->map_noise = 5e-3f;                  // params.h:93
+        cfg->cluster_half = (float)0.025;        // params.h:41
+        cfg->search_half = (float)0.025 * 3.0;   // GPisMap3.cpp:811  C_leng*3.0
+        cfg->var_thre = 0.5f;                    // GPisMap3.cpp:800
+    } else {
+        cfg->map_scale = 1.2f;                   // params.h:73
+        cfg->map_noise = 1e-2f;                  // params.h:74
+        cfg->cluster_half = (float)0.8;          // params.h:34
+        cfg->search_half = 1.2f * 4.0;           // GPisMap.cpp:680   map_scale_param*4.0
+        cfg->var_thre = 0.4f;                    // GPisMap.cpp:671
+    }
+    cfg->obs_scale = 0.5f;                       // params.h:97
+    cfg->obs_noise = 0.01f;                      // params.h:98
+    cfg->max_leaves = 1 << 16;
+    cfg->arena_chunk_bytes = 1ull << 30;
+    return GPIS_OK;
+}
+
+int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
+    if (!out || !cfg || (cfg->dim != 2 && cfg->dim != 3)) return GPIS_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return GPIS_ERR_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return GPIS_ERR_NODEVICE;
+    if (prop.major != 10) {
+        std::fprintf(stderr, "gpis_b200: device %d is sm_%d%d; this library is built for sm_100a only and has no fallback\n",
+                     cfg->device, prop.major, prop.minor);
+        return GPIS_ERR_NODEVICE;
+    }
+    gpis_ctx* ctx = new gpis_ctx();
+    ctx->cfg = *cfg;
+    if (ctx->cfg.arena_chunk_bytes < (64ull << 20)) ctx->cfg.arena_chunk_bytes = 64ull << 20;
+    *out = ctx;
+    CK(cudaSetDevice(cfg->device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ctx->ev[i]));
+    derive_params(ctx);
+    uint32_t cap = 4096;
+    while (cap < (uint32_t)std::max(1, cfg->max_leaves) * 2u) cap *= 2;
+    int rc = table_alloc(ctx, cap, std::max(1024, cfg->max_leaves));
+    if (rc) return rc;
+    CK(cudaFuncSetAttribute(k_leaf_train, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_eval_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    rc = query_v2_init(ctx->err);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPIS_OK;
+}
+
+void gpis_destroy(gpis_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& c : ctx->chunks) cudaFree(c.base);
+    cudaFree(ctx->T.keys); cudaFree(ctx->T.vals); cudaFree(ctx->T.centre); cudaFree(ctx->T.cell);
+    cudaFree(ctx->T.rec); cudaFree(ctx->T.meta); cudaFree(ctx->T.lo); cudaFree(ctx->T.hi);
+    cudaFree(ctx->d_scratch); cudaFree(ctx->d_scratch2);
+    cudaFree(ctx->W.cand); cudaFree(ctx->W.tie); cudaFree(ctx->W.evalout); cudaFree(ctx->W.pairs); cudaFree(ctx->W.counters);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
+    cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
+    cudaFree(ctx->d_export);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* gpis_last_error(const gpis_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int gpis_device(const gpis_ctx* ctx) { return ctx ? ctx->cfg.device : -1; }
+
+int gpis_reset(gpis_ctx* ctx) {
+    if (!ctx) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->leaves.clear();
+    ctx->free_slots.clear();
+    ctx->slot_count = 0;
+    ctx->tombs = 0;
+    ctx->free_blocks.clear();
+    for (auto& c : ctx->chunks) ctx->free_blocks[(uint64_t)c.base] = c.size;
+    ctx->arena_used = 0;
+    CK(cudaMemsetAsync(ctx->T.keys, 0, sizeof(uint64_t) * ctx->table_cap, ctx->stream));
+    CK(cudaMemsetAsync(ctx->T.cell, 0, sizeof(int4) * ctx->slot_cap, ctx->stream));
+    CK(cudaMemsetAsync(ctx->T.rec, 0, sizeof(uint64_t) * ctx->slot_cap, ctx->stream));
+    ctx->obs_trained = false;
+    ctx->obs_repartition = true;   // ObsGP2D::reset (ObsGP.cpp:198-203) runs when the map deletes gpo
+    ctx->obs_ni = ctx->obs_nj = -1;
+    ctx->dirty_keys.clear();
+    ctx->max_nb = 1; ctx->max_N = 1;
+    derive_params(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPIS_OK;
+}
+
+int gpis_rebase(gpis_ctx* ctx, const int32_t* root_min_cell, int levels) {
+    if (!ctx || !root_min_cell || levels < 0 || levels > 20) return GPIS_ERR_ARG;
+    for (int c = 0; c < 3; ++c) ctx->qp.root_min[c] = (c < ctx->cfg.dim) ? root_min_cell[c] : 0;
+    ctx->qp.levels = levels;
+    return GPIS_OK;
+}
+
+// gradflag rule shared with the kernel (OnGPIS.cpp:63-66, 122-125)
+static inline bool grad_valid(const float* s, int dim) {
+    bool allsmall = true;
+    for (int c = 0; c < dim; ++c) allsmall = allsmall && (std::fabs((double)s[dim + c]) < 1e-6);
+    return !((double)s[2 * dim + 2] > 0.1001 || allsmall);
+}
+
+static int apply_updates(gpis_ctx* ctx, const std::vector<SlotUpdate>& ups) {
+    if (ups.empty()) return 0;
+    int rc = ensure(ctx, &ctx->d_scratch2, &ctx->scratch2_bytes, ups.size() * sizeof(SlotUpdate));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_scratch2, ups.data(), ups.size() * sizeof(SlotUpdate), cudaMemcpyHostToDevice, ctx->stream));
+    k_table_apply<<<((int)ups.size() + 127) / 128, 128, 0, ctx->stream>>>(ctx->T, (const SlotUpdate*)ctx->d_scratch2, (int)ups.size());
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// centre / default box of a leaf; keeps an explicitly set box (gpis_leaves_set_boxes)
+static void set_geometry(gpis_ctx* ctx, HostLeaf& hl, const int32_t* cell, const float* centre) {
+    const int dim = ctx->cfg.dim;
+    for (int c = 0; c < 3; ++c) { hl.cell[c] = 0; hl.centre[c] = 0.f; }
+    for (int c = 0; c < dim; ++c) { hl.cell[c] = cell[c]; hl.centre[c] = centre[c]; }
+    if (!hl.box_set)
+        for (int c = 0; c < 3; ++c) {
+            hl.lo[c] = (c < dim) ? hl.centre[c] - ctx->cfg.cluster_half : 0.f;   // octree.h:73-78
+            hl.hi[c] = (c < dim) ? hl.centre[c] + ctx->cfg.cluster_half : 0.f;
+        }
+}
+static SlotUpdate make_update(uint64_t key, const HostLeaf& hl) {
+    SlotUpdate u{};
+    u.key = key; u.rec = hl.rec; u.slot = hl.slot; u.live = 1;
+    for (int c = 0; c < 3; ++c) { u.cell[c] = hl.cell[c]; u.centre[c] = hl.centre[c]; u.lo[c] = hl.lo[c]; u.hi[c] = hl.hi[c]; }
+    u.meta[0] = hl.N; u.meta[1] = hl.ng; u.meta[2] = hl.n; u.meta[3] = hl.nb;
+    return u;
+}
+
+static int take_slot(gpis_ctx* ctx) {
+    if (!ctx->free_slots.empty()) { int s = ctx->free_slots.back(); ctx->free_slots.pop_back(); return s; }
+    return ctx->slot_count++;
+}
+
+int gpis_leaves_mark(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres) {
+    if (!ctx || n_leaves < 0 || (n_leaves > 0 && (!cells || !centres))) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim;
+    int rc = table_reserve(ctx, n_leaves);
+    if (rc) return rc;
+    std::vector<SlotUpdate> ups;
+    for (int i = 0; i < n_leaves; ++i) {
+        const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
+        if (ctx->leaves.count(key)) continue;
+        HostLeaf hl{};
+        hl.slot = take_slot(ctx);
+        set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
+        ctx->leaves[key] = hl;
+        ups.push_back(make_update(key, hl));
+    }
+    return apply_updates(ctx, ups);
+}
+
+int gpis_leaves_set_boxes(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* boxes) {
+    if (!ctx || n_leaves < 0 || (n_leaves > 0 && (!cells || !boxes))) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim;
+    std::vector<SlotUpdate> ups;
+    for (int i = 0; i < n_leaves; ++i) {
+        const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
+        auto it = ctx->leaves.find(key);
+        if (it == ctx->leaves.end()) continue;
+        HostLeaf& hl = it->second;
+        for (int c = 0; c < dim; ++c) { hl.lo[c] = boxes[(size_t)i * 2 * dim + c]; hl.hi[c] = boxes[(size_t)i * 2 * dim + dim + c]; }
+        hl.box_set = true;
+        ups.push_back(make_update(key, hl));
+    }
+    return apply_updates(ctx, ups);
+}
+
+int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
+    if (!ctx || n_leaves < 0 || (n_leaves > 0 && !cells)) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim;
+    std::vector<SlotUpdate> ups;
+    for (int i = 0; i < n_leaves; ++i) {
+        const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
+        auto it = ctx->leaves.find(key);
+        if (it == ctx->leaves.end()) continue;
+        SlotUpdate u{};
+        u.key = key; u.slot = it->second.slot; u.live = 0;
+        ups.push_back(u);
+        if (it->second.rec) arena_free(ctx, it->second.rec, it->second.rec_bytes);
+        ctx->free_slots.push_back(it->second.slot);
+        ctx->leaves.erase(it);
+        ctx->tombs++;
+    }
+    int rc = apply_updates(ctx, ups);
+    if (rc) return rc;
+    if (ctx->tombs * 4 > (int)ctx->table_cap) return table_alloc(ctx, ctx->table_cap, ctx->slot_cap);
+    return 0;
+}
+
+int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres,
+                       const int32_t* offsets, const float* samples, int32_t* status) {
+    if (!ctx || n_leaves < 0) return GPIS_ERR_ARG;
+    if (n_leaves == 0) return GPIS_OK;
+    if (!cells || !centres || !offsets || !samples) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
+    int rc = table_reserve(ctx, n_leaves);
+    if (rc) return rc;
+
+    std::vector<TrainJob> jobs;
+    std::vector<int> job_leaf;
+    std::vector<SlotUpdate> ups;
+    std::vector<std::pair<uint64_t, uint64_t>> to_free;
+    double flops = 0, bytes = 0;
+    int64_t sumN = 0, sumn = 0;
+    int maxN = 1, maxnb = 1;
+    for (int i = 0; i < n_leaves; ++i) {
+        const int N = offsets[i + 1] - offsets[i];
+        if (N < 0) { ctx->err = "offsets must be non-decreasing"; return GPIS_ERR_ARG; }
+        if (N > GPIS_MAX_SAMPLES) { ctx->err = "leaf exceeds GPIS_MAX_SAMPLES"; return GPIS_ERR_CAPACITY; }
+        const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
+        auto it = ctx->leaves.find(key);
+        if (it == ctx->leaves.end()) {
+            HostLeaf hl{};
+            hl.slot = take_slot(ctx);
+            it = ctx->leaves.emplace(key, hl).first;
+        }
+        HostLeaf& hl = it->second;
+        set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
+        if (status) status[i] = 0;
+        if (N == 0) {  // GPisMap3.cpp:710: nothing in range -> the leaf keeps whatever GP it had
+            ups.push_back(make_update(key, hl));
+            continue;
+        }
+        int ng = 0;
+        for (int k = 0; k < N; ++k) ng += grad_valid(samples + (size_t)(offsets[i] + k) * w9, dim) ? 1 : 0;
+        const int n = N + dim * ng, nb = (n + 31) / 32;
+        if (n > GPIS_MAX_N) { ctx->err = "leaf exceeds GPIS_MAX_N"; return GPIS_ERR_CAPACITY; }
+        uint64_t rec = 0;
+        const uint64_t rb = rec_bytes(N, nb);
+        rc = arena_alloc(ctx, rb, &rec);
+        if (rc) return rc;
+        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
+        hl.rec = rec; hl.rec_bytes = rb; hl.N = N; hl.ng = ng; hl.n = n; hl.nb = nb;
+        TrainJob j{};
+        j.rec = rec; j.sample_off = offsets[i]; j.N = N; j.ng = ng; j.n = n; j.nb = nb; j.slot = hl.slot;
+        for (int c = 0; c < 3; ++c) { j.cell[c] = hl.cell[c]; j.centre[c] = hl.centre[c]; }
+        jobs.push_back(j);
+        job_leaf.push_back(i);
+        ups.push_back(make_update(key, hl));
+        ctx->dirty_keys.push_back(key);
+        flops += (double)n * n * n / 3.0 + 2.0 * n * n + 30.0 * N * N;
+        bytes += 52.0 * N + 4.0 * n + 2.0 * n * (n + 1.0);
+        sumN += N; sumn += n;
+        maxN = std::max(maxN, N); maxnb = std::max(maxnb, nb);
+    }
+    ctx->max_nb = std::max(ctx->max_nb, maxnb);
+    ctx->max_N = std::max(ctx->max_N, maxN);
+
+    float ms = 0.f;
+    if (!jobs.empty()) {
+        // biggest systems first: one CTA per leaf, the hardware scheduler balances the tail
+        std::vector<int> order(jobs.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].n > jobs[b].n; });
+        std::vector<TrainJob> sorted(jobs.size());
+        for (size_t i = 0; i < order.size(); ++i) sorted[i] = jobs[order[i]];
+        const uint64_t nsamp = (uint64_t)offsets[n_leaves];
+        const uint64_t b_jobs = align_up(sorted.size() * sizeof(TrainJob), 256);
+        const uint64_t b_smp = align_up(nsamp * w9 * sizeof(float), 256);
+        const uint64_t b_st = align_up(sorted.size() * sizeof(int32_t), 256);
+        rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, b_jobs + b_smp + b_st);
+        if (rc) return rc;
+        unsigned char* base = (unsigned char*)ctx->d_scratch;
+        TrainJob* d_jobs = (TrainJob*)base;
+        float* d_smp = (float*)(base + b_jobs);
+        int32_t* d_st = (int32_t*)(base + b_jobs + b_smp);
+        CK(cudaMemcpyAsync(d_jobs, sorted.data(), sorted.size() * sizeof(TrainJob), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_smp, samples, nsamp * w9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        const int smem = TrainSmem::total(maxN, maxnb);
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_leaf_train<<<(int)sorted.size(), TRAIN_THREADS, smem, ctx->stream>>>(d_jobs, d_smp, ctx->tp, d_st);
+        ctx->st.kernel_launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        std::vector<int32_t> st(sorted.size());
+        CK(cudaMemcpyAsync(st.data(), d_st, sorted.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        if (status)
+            for (size_t i = 0; i < order.size(); ++i) status[job_leaf[order[i]]] = st[i];
+    }
+    rc = apply_updates(ctx, ups);   // install after training: queries never see a half-built record
+    if (rc) return rc;
+    for (auto& f : to_free) arena_free(ctx, f.first, f.second);
+    ctx->st.last_train_leaves = (int64_t)jobs.size();
+    ctx->st.last_train_sum_N = sumN; ctx->st.last_train_sum_n = sumn;
+    ctx->st.last_train_flops = flops; ctx->st.last_train_bytes = bytes;
+    ctx->st.last_train_ms = ms;
+    return GPIS_OK;
+}
+
+int gpis_leaf_index(gpis_ctx* ctx, const int32_t* cell) {
+    if (!ctx || !cell) return -1;
+    auto it = ctx->leaves.find(key_of(ctx, cell));
+    return it == ctx->leaves.end() ? -1 : it->second.slot;
+}
+
+int gpis_leaf_get(gpis_ctx* ctx, const int32_t* cell, int32_t* N, int32_t* ng, float* alpha, float* L,
+                  float* gradflag, int cap_n) {
+    if (!ctx || !cell) return 0;
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return 0;
+    auto it = ctx->leaves.find(key_of(ctx, cell));
+    if (it == ctx->leaves.end() || it->second.rec == 0) return 0;
+    const HostLeaf& hl = it->second;
+    if (N) *N = hl.N;
+    if (ng) *ng = hl.ng;
+    if (hl.n > cap_n) return hl.n;
+    const unsigned char* rec = (const unsigned char*)hl.rec;
+    if (alpha) {
+        if (cudaMemcpy(alpha, rec + rec_off_alpha(hl.N), sizeof(float) * hl.n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    }
+    if (gradflag) {
+        std::vector<float4> pts(hl.N);
+        if (cudaMemcpy(pts.data(), rec + rec_off_pts(), sizeof(float4) * hl.N, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        for (int k = 0; k < hl.N; ++k) { int g; std::memcpy(&g, &pts[k].w, 4); gradflag[k] = g >= 0 ? 1.f : 0.f; }
+    }
+    if (L) {
+        if (ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, sizeof(float) * (uint64_t)hl.n * hl.n)) return 0;
+        const int tot = hl.n * hl.n;
+        k_unpack_L<<<(tot + 255) / 256, 256, 0, ctx->stream>>>((const float*)(rec + rec_off_tiles(hl.N, hl.nb)), hl.n, hl.nb, (float*)ctx->d_scratch);
+        ctx->st.kernel_launches++;
+        if (cudaMemcpyAsync(L, ctx->d_scratch, sizeof(float) * (uint64_t)tot, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+    }
+    return hl.n;
+}
+
+// ------------------------------------------------------------------ queries
+static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, int32_t* h_chosen, int32_t* h_tie) {
+    const int dim = ctx->cfg.dim;
+    const int64_t CH = 1 << 22;  // queries per chunk (bounds scratch: ~160 B/query)
+    const int64_t chunk_cap = std::min<int64_t>(n, CH);
+    if (ctx->work_cap < chunk_cap) {
+        cudaFree(ctx->W.cand); cudaFree(ctx->W.tie); cudaFree(ctx->W.evalout); cudaFree(ctx->W.pairs); cudaFree(ctx->W.counters);
+        ctx->W = QueryWork{};
+        ctx->work_cap = 0;
+        const int64_t cap = chunk_cap + chunk_cap / 8 + 1024;
+        CK(cudaMalloc(&ctx->W.cand, sizeof(int4) * cap));
+        CK(cudaMalloc(&ctx->W.tie, sizeof(int32_t) * cap));
+        CK(cudaMalloc(&ctx->W.evalout, sizeof(float) * 24 * cap));
+        CK(cudaMalloc(&ctx->W.pairs, sizeof(int2) * 2 * cap));
+        CK(cudaMalloc(&ctx->W.counters, sizeof(int32_t) * 16));
+        ctx->work_cap = cap;
+    }
+    QueryWork W = ctx->W;
+    if (!h_tie) W.tie = nullptr;
+    double flops = 0, bytes_g = 0;
+    int64_t evals = 0;
+    float ms_total = 0.f, ms_eval = 0.f;
+    std::vector<int2> hpairs;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int64_t q0 = 0; q0 < n; q0 += CH) {
+        const int64_t nq = std::min<int64_t>(CH, n - q0);
+        const float* xq = d_x + q0 * dim;
+        float* rq = d_res + q0 * 2 * (1 + dim);
+        const int gq = (int)((nq + 255) / 256);
+        CK(cudaMemsetAsync(W.counters, 0, sizeof(int32_t) * 16, ctx->stream));
+        k_candidates<<<gq, 256, 0, ctx->stream>>>(xq, nq, rq, ctx->T, ctx->qp, W);
+        ctx->st.kernel_launches++;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                CK(cudaMemsetAsync(W.counters, 0, sizeof(int32_t) * 16, ctx->stream));
+                k_select2<<<gq, 256, 0, ctx->stream>>>(nq, rq, ctx->T, ctx->qp, W, 0);
+                ctx->st.kernel_launches++;
+            }
+            int32_t npairs = 0;
+            CK(cudaMemcpyAsync(&npairs, W.counters, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (npairs > 0) {
+                CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+                if (ctx->eval_version == 1) {
+                    const int smem = (1 + dim) * ctx->max_nb * 32 * (int)sizeof(float);
+                    for (int p0 = 0; p0 < npairs; p0 += 1 << 30) {
+                        k_eval_v1<<<npairs, EVAL1_THREADS, smem, ctx->stream>>>(xq, ctx->T, ctx->qp, W, 0);
+                        ctx->st.kernel_launches++;
+                    }
+                } else {
+                    int rc = query_v2_eval(ctx->stream, xq, ctx->T, ctx->qp, W, npairs, ctx->slot_count, ctx->max_nb,
+                                           &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err);
+                    if (rc) return rc;
+                }
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                ms_eval += ms;
+                evals += npairs;
+            }
+        }
+        k_fuse<<<gq, 256, 0, ctx->stream>>>(nq, rq, ctx->T, ctx->qp, W);
+        ctx->st.kernel_launches++;
+        CK(cudaGetLastError());
+        if (h_chosen) CK(cudaMemcpyAsync(h_chosen + q0 * 4, W.cand, sizeof(int4) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_tie) CK(cudaMemcpyAsync(h_tie + q0, W.tie, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_chosen || h_tie) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[1]));
+    ctx->st.last_query_n = n;
+    ctx->st.last_query_evals = evals;
+    ctx->st.last_query_ms = ms_total;
+    ctx->st.last_query_eval_ms = ms_eval;
+    (void)flops; (void)bytes_g;
+    return GPIS_OK;
+}
+
+int gpis_query_device(gpis_ctx* ctx, const float* x_device, int64_t n, float* res_inout_device) {
+    if (!ctx || !x_device || !res_inout_device || n < 1) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    return query_core(ctx, x_device, n, res_inout_device, nullptr, nullptr);
+}
+
+static int query_host(gpis_ctx* ctx, const float* x, int64_t n, float* res, int32_t* chosen, int32_t* tie) {
+    if (!ctx || !x || !res || n < 1) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim, w2 = 2 * (1 + dim);
+    if (ctx->q_cap < n) {
+        cudaFree(ctx->d_x); cudaFree(ctx->d_res);
+        ctx->d_x = ctx->d_res = nullptr; ctx->q_cap = 0;
+        CK(cudaMalloc(&ctx->d_x, sizeof(float) * dim * n));
+        CK(cudaMalloc(&ctx->d_res, sizeof(float) * w2 * n));
+        ctx->q_cap = n;
+    }
+    CK(cudaMemcpyAsync(ctx->d_x, x, sizeof(float) * dim * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_res, res, sizeof(float) * w2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = query_core(ctx, (const float*)ctx->d_x, n, (float*)ctx->d_res, chosen, tie);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(res, ctx->d_res, sizeof(float) * w2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPIS_OK;
+}
+int gpis_query(gpis_ctx* ctx, const float* x, int64_t n, float* res_inout) { return query_host(ctx, x, n, res_inout, nullptr, nullptr); }
+int gpis_query_debug(gpis_ctx* ctx, const float* x, int64_t n, float* res_inout, int32_t* chosen4, int32_t* tie) {
+    return query_host(ctx, x, n, res_inout, chosen4, tie);
+}
+
+// ------------------------------------------------------------------ observation GPs
+static int obs_upload_partition(gpis_ctx* ctx) {
+    const int nt = (int)ctx->obs_hdesc.size();
+    if (nt > ctx->obs_tile_cap) {
+        cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc);
+        ctx->obs_tiles = nullptr; ctx->obs_desc = nullptr; ctx->obs_tile_cap = 0;
+        CK(cudaMalloc(&ctx->obs_tiles, sizeof(ObsTile) * nt));
+        CK(cudaMalloc(&ctx->obs_desc, sizeof(ObsTileDesc) * nt));
+        ctx->obs_tile_cap = nt;
+    }
+    const int nbv = (int)std::max(ctx->obs_hb0.size(), ctx->obs_hb1.size());
+    if (nbv > ctx->obs_b_cap) {
+        cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
+        ctx->obs_b0 = ctx->obs_b1 = nullptr; ctx->obs_b_cap = 0;
+        CK(cudaMalloc(&ctx->obs_b0, sizeof(float) * nbv));
+        CK(cudaMalloc(&ctx->obs_b1, sizeof(float) * nbv));
+        ctx->obs_b_cap = nbv;
+    }
+    if (nt) CK(cudaMemcpyAsync(ctx->obs_desc, ctx->obs_hdesc.data(), sizeof(ObsTileDesc) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->obs_hb0.empty()) CK(cudaMemcpyAsync(ctx->obs_b0, ctx->obs_hb0.data(), sizeof(float) * ctx->obs_hb0.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->obs_hb1.empty()) CK(cudaMemcpyAsync(ctx->obs_b1, ctx->obs_hb1.data(), sizeof(float) * ctx->obs_hb1.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int gpis_obs_train_2d(gpis_ctx* ctx, const float* vu, const float* zinv, int ni, int nj) {
+    if (!ctx) return GPIS_ERR_ARG;
+    if (!vu || !zinv || ni <= 0 || nj <= 0) return GPIS_OK;   // ObsGP.cpp:333: silently untrained
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int g = 5, ov = 3;                                   // params.h:109-110
+    ctx->op.d = 2; ctx->op.ni = ni; ctx->op.margin = 0.005f;   // params.h:108
+    if (ctx->obs_ni != ni || ctx->obs_nj != nj || ctx->obs_repartition) {
+        // computePartition, ObsGP.cpp:204-265
+        const int ng0 = (ni - ov) / g + 1, ng1 = (nj - ov) / g + 1;
+        if (ng0 < 1 || ng1 < 1) { ctx->err = "grid too small for the ObsGP partition"; return GPIS_ERR_ARG; }
+        std::vector<int> i0(ng0), i1(ng0), j0(ng1), j1(ng1);
+        ctx->obs_hb0.assign(1, vu[0]);
+        for (int n = 0; n < ng0; ++n) {
+            i0[n] = n * g; i1[n] = i0[n] + g + ov - 1;
+            if (n < ng0 - 1) ctx->obs_hb0.push_back(vu[2 * (i1[n] - ov / 2)]);
+            else { i1[n] = ni - 1; ctx->obs_hb0.push_back(vu[2 * i1[n]]); }
+        }
+        ctx->obs_hb1.assign(1, vu[1]);
+        for (int m = 0; m < ng1; ++m) {
+            j0[m] = m * g; j1[m] = j0[m] + g + ov - 1;
+            if (m < ng1 - 1) ctx->obs_hb1.push_back(vu[2 * (size_t)(j1[m] - ov / 2) * ni + 1]);
+            else { j1[m] = nj - 1; ctx->obs_hb1.push_back(vu[2 * (size_t)j1[m] * ni + 1]); }
+        }
+        ctx->obs_hdesc.clear();
+        for (int m = 0; m < ng1; ++m)
+            for (int n = 0; n < ng0; ++n) ctx->obs_hdesc.push_back(ObsTileDesc{i0[n], i1[n], j0[m], j1[m]});
+        ctx->op.ng0 = ng0; ctx->op.ntiles = ng0 * ng1;
+        ctx->op.nb0 = (int)ctx->obs_hb0.size(); ctx->op.nb1 = (int)ctx->obs_hb1.size();
+        ctx->obs_ni = ni; ctx->obs_nj = nj; ctx->obs_repartition = false;
+        int rc = obs_upload_partition(ctx);
+        if (rc) return rc;
+    }
+    const uint64_t bx = align_up(sizeof(float) * 2 * (uint64_t)ni * nj, 256), bf = align_up(sizeof(float) * (uint64_t)ni * nj, 256);
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, bx + bf);
+    if (rc) return rc;
+    float* d_vu = (float*)ctx->d_scratch;
+    float* d_f = (float*)((unsigned char*)ctx->d_scratch + bx);
+    CK(cudaMemcpyAsync(d_vu, vu, sizeof(float) * 2 * (uint64_t)ni * nj, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_f, zinv, sizeof(float) * (uint64_t)ni * nj, cudaMemcpyHostToDevice, ctx->stream));
+    k_obs_train<<<ctx->op.ntiles, OBS_MAXP, 0, ctx->stream>>>(d_vu, d_f, ctx->obs_desc, ctx->obs_tiles, ctx->op);
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->obs_trained = true;
+    return GPIS_OK;
+}
+
+int gpis_obs_train_1d(gpis_ctx* ctx, const float* theta, const float* f, int N) {
+    if (!ctx) return GPIS_ERR_ARG;
+    if (!theta || !f || N <= 0) return GPIS_OK;                // ObsGP.cpp:89
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int g = 20, ov = 6;                                  // params.h:101-102
+    ctx->op.d = 1; ctx->op.ni = N; ctx->op.margin = 0.0175f;   // params.h:103
+    // group ranges, ObsGP.cpp:91-137 (recomputed every frame: ObsGP1D::reset clears `range`)
+    const int nGroup = N / g + 1;
+    ctx->obs_hb0.assign(1, theta[0]);
+    ctx->obs_hb1.clear();
+    ctx->obs_hdesc.clear();
+    for (int n = 0; n < nGroup - 1; ++n) {
+        if (n < nGroup - 2) {
+            const int a = n * g, b = a + g + ov;
+            ctx->obs_hb0.push_back(theta[b - ov / 2]);
+            ctx->obs_hdesc.push_back(ObsTileDesc{a, a + g + ov - 1, 0, 0});
+        } else {
+            int a = n * g;
+            int b = a + (N - a) / 2 + ov;
+            ctx->obs_hb0.push_back(theta[b - ov / 2]);
+            ctx->obs_hdesc.push_back(ObsTileDesc{a, b, 0, 0});
+            ++n;
+            a = a + (N - a) / 2;
+            b = N - 1;
+            ctx->obs_hb0.push_back(theta[b]);
+            ctx->obs_hdesc.push_back(ObsTileDesc{a, b, 0, 0});
+        }
+    }
+    ctx->op.ng0 = (int)ctx->obs_hdesc.size(); ctx->op.ntiles = (int)ctx->obs_hdesc.size();
+    ctx->op.nb0 = (int)ctx->obs_hb0.size(); ctx->op.nb1 = 0;
+    ctx->obs_ni = -1; ctx->obs_nj = -1; ctx->obs_repartition = true;
+    int rc = obs_upload_partition(ctx);
+    if (rc) return rc;
+    const uint64_t bx = align_up(sizeof(float) * (uint64_t)N, 256);
+    rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, 2 * bx);
+    if (rc) return rc;
+    float* d_t = (float*)ctx->d_scratch;
+    float* d_f = (float*)((unsigned char*)ctx->d_scratch + bx);
+    CK(cudaMemcpyAsync(d_t, theta, sizeof(float) * N, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_f, f, sizeof(float) * N, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->op.ntiles > 0) {
+        k_obs_train<<<ctx->op.ntiles, OBS_MAXP, 0, ctx->stream>>>(d_t, d_f, ctx->obs_desc, ctx->obs_tiles, ctx->op);
+        ctx->st.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->obs_trained = true;
+    return GPIS_OK;
+}
+
+int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, float* var) {
+    if (!ctx || !xt || !val || !var || m < 0) return GPIS_ERR_ARG;
+    if (m == 0) return GPIS_OK;
+    if (!ctx->obs_trained) return GPIS_OK;                    // ObsGP.cpp:147-149, 412-414: outputs untouched
+    if (d != ctx->op.d) return GPIS_OK;                       // ObsGP.cpp:412: wrong input dimension
+    CK(cudaSetDevice(ctx->cfg.device));
+    const uint64_t bx = align_up(sizeof(float) * (uint64_t)d * m, 256), bv = align_up(sizeof(float) * (uint64_t)m, 256);
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, bx + 2 * bv);
+    if (rc) return rc;
+    float* d_x = (float*)ctx->d_scratch;
+    float* d_val = (float*)((unsigned char*)ctx->d_scratch + bx);
+    float* d_var = (float*)((unsigned char*)ctx->d_scratch + bx + bv);
+    CK(cudaMemcpyAsync(d_x, xt, sizeof(float) * (uint64_t)d * m, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_val, val, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
+    const int warps_per_block = 8;
+    k_obs_test<<<(m + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->stream>>>(
+        d_x, m, ctx->obs_b0, ctx->obs_b1, ctx->obs_tiles, ctx->op, d_val, d_var);
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(val, d_val, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(var, d_var, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPIS_OK;
+}
+
+// ------------------------------------------------------------------ replication + stats
+int gpis_export_dirty(gpis_ctx* ctx, const void** buf_device, uint64_t* bytes) {
+    if (!ctx || !buf_device || !bytes) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    // de-duplicate, keep only keys that still hold a record
+    std::vector<uint64_t> keys;
+    {
+        std::unordered_map<uint64_t, int> seen;
+        for (uint64_t k : ctx->dirty_keys) {
+            auto it = ctx->leaves.find(k);
+            if (it == ctx->leaves.end() || it->second.rec == 0) continue;
+            if (seen.emplace(k, 1).second) keys.push_back(k);
+        }
+    }
+    uint64_t total = 0;
+    for (uint64_t k : keys) total += align_up(ctx->leaves[k].rec_bytes, 256);
+    int rc = ensure(ctx, &ctx->d_export, &ctx->export_cap, std::max<uint64_t>(total, 256));
+    if (rc) return rc;
+    uint64_t off = 0;
+    for (uint64_t k : keys) {
+        const HostLeaf& hl = ctx->leaves[k];
+        CK(cudaMemcpyAsync((unsigned char*)ctx->d_export + off, (const void*)hl.rec, hl.rec_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        off += align_up(hl.rec_bytes, 256);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dirty_keys.clear();
+    *buf_device = ctx->d_export;
+    *bytes = total;
+    return GPIS_OK;
+}
+
+int gpis_import(gpis_ctx* ctx, const void* buf_device, uint64_t bytes) {
+    if (!ctx || (bytes && !buf_device)) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim;
+    uint64_t off = 0;
+    std::vector<SlotUpdate> ups;
+    std::vector<std::pair<uint64_t, uint64_t>> to_free;
+    while (off + sizeof(LeafHeader) <= bytes) {
+        LeafHeader h;
+        CK(cudaMemcpy(&h, (const unsigned char*)buf_device + off, sizeof(h), cudaMemcpyDeviceToHost));
+        if (h.bytes == 0 || off + h.bytes > bytes) break;
+        int rc = table_reserve(ctx, 1);
+        if (rc) return rc;
+        auto it = ctx->leaves.find(h.key);
+        if (it == ctx->leaves.end()) {
+            HostLeaf hl{};
+            hl.slot = take_slot(ctx);
+            it = ctx->leaves.emplace(h.key, hl).first;
+        }
+        HostLeaf& hl = it->second;
+        uint64_t rec = 0;
+        rc = arena_alloc(ctx, h.bytes, &rec);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync((void*)rec, (const unsigned char*)buf_device + off, h.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
+        hl.rec = rec; hl.rec_bytes = h.bytes; hl.N = h.N; hl.ng = h.ng; hl.n = h.n; hl.nb = h.nb;
+        set_geometry(ctx, hl, h.cell, h.centre);
+        ctx->max_nb = std::max(ctx->max_nb, h.nb);
+        ctx->max_N = std::max(ctx->max_N, h.N);
+        ups.push_back(make_update(h.key, hl));
+        off += align_up(h.bytes, 256);
+    }
+    int rc = apply_updates(ctx, ups);
+    if (rc) return rc;
+    for (auto& f : to_free) arena_free(ctx, f.first, f.second);
+    return GPIS_OK;
+}
+
+int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out) {
+    if (!ctx || !out) return GPIS_ERR_ARG;
+    ctx->st.leaves = (int64_t)ctx->leaves.size();
+    int64_t tr = 0;
+    for (auto& kv : ctx->leaves) tr += kv.second.rec ? 1 : 0;
+    ctx->st.leaves_trained = tr;
+    ctx->st.arena_bytes_used = (int64_t)ctx->arena_used;
+    ctx->st.arena_bytes_reserved = (int64_t)ctx->arena_reserved;
+    *out = ctx->st;
+    return GPIS_OK;
+}
+
+int gpis_set_eval_version(gpis_ctx* ctx, int v) {
+    if (!ctx || (v != 1 && v != 2)) return GPIS_ERR_ARG;
+    ctx->eval_version = v;
+    return GPIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,469 @@
+// K1 — batched leaf-GP training: covFnc (train) + OnGPIS::train as one kernel, one CTA per dirty
+// leaf. Replaces cpp/src/covFnc.cpp:142-256 / 317-402 and cpp/src/OnGPIS.cpp:34-149.
+//
+// Per leaf (N samples, ng with a usable normal, n = N + dim*ng unknowns, nb = ceil(n/32)):
+//   A. load the samples, apply the gradflag rule (OnGPIS.cpp:63-66, 122-125), build y
+//   B. build K (lower triangle) straight into the leaf record's tile array — one double exp per
+//      ordered sample pair, entries rounded to float exactly like the reference (covFnc.cpp:29-33)
+//   C. left-looking blocked Cholesky, 32x32 tiles: for block column bj, every warp owns one tile
+//      (bi, bj) as a 4x8-per-lane register block and subtracts L(bi,bk) L(bj,bk)^T for bk < bj;
+//      the operand tiles stream L2/HBM -> shared memory through TMA bulk copies (double
+//      buffered, mbarrier completion). The diagonal tile is factored and inverted by one warp
+//      with shuffles; off-diagonal tiles are finished as acc * inv(Ljj)^T. The forward solve
+//      L z = y rides along (the needed tiles are already in shared memory).
+//   D. backward solve L^T alpha = z by block columns.
+// Bound: FP32 FMA pipe (n^3/3 flops vs ~2n^2 compulsory bytes). No tensor cores: these are
+// independent small factorizations in fp32 with a 1e-4 parity contract.
+#pragma once
+#include "common.cuh"
+
+namespace gpis {
+
+#define TRAIN_WARPS 8
+#define TRAIN_THREADS (TRAIN_WARPS * 32)
+#define TRAIN_STAGE_TILES (TRAIN_WARPS + 1)  // A tile per warp + the shared B tile
+
+struct TrainJob {
+    uint64_t rec;        // device address of the (pre-allocated) leaf record
+    int32_t sample_off;  // first sample in the batch's sample array
+    int32_t N;           // samples in the training ball
+    int32_t ng, n, nb;   // host-computed with the same gradflag rule
+    int32_t slot;
+    int32_t cell[3];
+    float centre[3];
+};
+
+struct TrainParams {
+    int dim;
+    float scale;   // map_scale_param
+    float a;       // (float)(sqrt(3)/scale)   covFnc.cpp:147
+    float a2;      // a*a
+};
+
+// dynamic shared memory layout (bytes)
+struct TrainSmem {
+    static constexpr int stage_bytes = TRAIN_STAGE_TILES * GPIS_TILE_BYTES;           // 36 KB
+    static constexpr int off_stage = 0;                                               // 2 stages
+    static constexpr int off_scratch = 0;   // per-warp 4 KB scratch aliases stage 0 (idle outside the bk loop)
+    static constexpr int off_dinv = 2 * stage_bytes;                                  // 4 KB
+    static constexpr int off_bar = off_dinv + GPIS_TILE_BYTES;                        // 2 mbarriers
+    static constexpr int off_misc = off_bar + 64;                                     // small arrays
+    // misc: pts float4[N] | sigx[N] | sigg[N] | y[nbmax*32] | z(=t) [nbmax*32] | wtot[32]
+    static int total(int Nmax, int nbmax) {
+        return off_misc + Nmax * 16 + Nmax * 4 * 2 + nbmax * 32 * 4 * 2 + 512;
+    }
+};
+
+// acc[i][j] -= sum_k A[k][4*rg+i] * B[k][8*cg+j]   (A, B: k-major 32x32 tiles in shared memory)
+__device__ __forceinline__ void tile_mma_sub(float (&acc)[4][8], const float* __restrict__ A,
+                                             const float* __restrict__ B, int rg, int cg) {
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(A + k * 32 + 4 * rg);
+        const float4 b0 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg);
+        const float4 b1 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg + 4);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(-av[i], bv[j], acc[i][j]);
+    }
+}
+// acc[i][j] += sum_k A[k][4*rg+i] * B[k][8*cg+j]
+__device__ __forceinline__ void tile_mma_add(float (&acc)[4][8], const float* __restrict__ A,
+                                             const float* __restrict__ B, int rg, int cg) {
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(A + k * 32 + 4 * rg);
+        const float4 b0 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg);
+        const float4 b1 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg + 4);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+// store / load a lane's 4x8 block to a k-major tile: element (r, c) at c*32 + r
+__device__ __forceinline__ void tile_store(float* T, const float (&acc)[4][8], int rg, int cg) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(T + (8 * cg + j) * 32 + 4 * rg) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+}
+__device__ __forceinline__ void tile_load(const float* T, float (&acc)[4][8], int rg, int cg) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(T + (8 * cg + j) * 32 + 4 * rg);
+        acc[0][j] = v.x; acc[1][j] = v.y; acc[2][j] = v.z; acc[3][j] = v.w;
+    }
+}
+
+// In-warp Cholesky of the 32x32 tile S (k-major in shared memory; only the lower triangle is
+// meaningful) followed by the inverse of the factor. Lane r keeps row r in registers; columns are
+// exchanged with shuffles. Writes L (lower, zeros above) back to S and inv(L) to Dinv (k-major).
+// Returns the number of non-positive pivots seen by this tile.
+__device__ __forceinline__ int warp_chol_inv(float* S, float* Dinv, int lane) {
+    float row[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) row[c] = S[c * 32 + lane];
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float djj = __shfl_sync(0xffffffffu, row[j], j);
+        if (!(djj > 0.f)) ++bad;
+        const float d = sqrtf(djj);
+        const float l = (lane == j) ? d : row[j] / d;
+        row[j] = (lane >= j) ? l : 0.f;
+#pragma unroll
+        for (int c = j + 1; c < 32; ++c) {
+            const float lc = __shfl_sync(0xffffffffu, l, c);  // L[c][j]
+            row[c] = fmaf(-l, lc, row[c]);                    // only rows >= c are meaningful
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) S[c * 32 + lane] = (lane >= c) ? row[c] : 0.f;
+    // inverse: lane c solves L x = e_c by forward substitution; x[r] kept in registers.
+    // L[r][k] is read from S (k-major): all lanes read the same address (broadcast).
+    __syncwarp();
+    float x[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        float s = (r == lane) ? 1.f : 0.f;
+#pragma unroll
+        for (int k = 0; k < r; ++k) s = fmaf(-S[k * 32 + r], x[k], s);
+        x[r] = s / S[r * 32 + r];
+    }
+    // X[r][c] = x[r] held by lane c  ->  k-major element (r, c) at c*32 + r
+#pragma unroll
+    for (int r = 0; r < 32; ++r) Dinv[lane * 32 + r] = (r >= lane) ? x[r] : 0.f;
+    return bad;
+}
+
+__global__ void __launch_bounds__(TRAIN_THREADS, 2)
+k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ samples, TrainParams P,
+             int32_t* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TrainJob job = jobs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = lane >> 2, cg = lane & 3;
+    const int dim = P.dim, N = job.N, ng = job.ng, n = job.n, nb = job.nb;
+    const int w9 = 2 * dim + 3;
+
+    float* stage[2] = {reinterpret_cast<float*>(smem_raw + TrainSmem::off_stage),
+                       reinterpret_cast<float*>(smem_raw + TrainSmem::off_stage + TrainSmem::stage_bytes)};
+    float* scratch = reinterpret_cast<float*>(smem_raw + TrainSmem::off_scratch) + warp * GPIS_TILE_ELEMS;
+    float* dinv_s = reinterpret_cast<float*>(smem_raw + TrainSmem::off_dinv);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TrainSmem::off_bar);
+    float4* pts = reinterpret_cast<float4*>(smem_raw + TrainSmem::off_misc);
+    float* sigx = reinterpret_cast<float*>(pts + N);
+    float* sigg = sigx + N;
+    float* yv = sigg + N;            // nb*32
+    float* zv = yv + nb * 32;        // nb*32 : running t = y - sum L z, then z, then alpha
+    int* wtot = reinterpret_cast<int*>(zv + nb * 32);
+
+    unsigned char* rec = reinterpret_cast<unsigned char*>(job.rec);
+    float4* rec_pts = reinterpret_cast<float4*>(rec + rec_off_pts());
+    float* rec_alpha = reinterpret_cast<float*>(rec + rec_off_alpha(N));
+    float* rec_dinv = reinterpret_cast<float*>(rec + rec_off_dinv(N, nb));
+    float* rec_tiles = reinterpret_cast<float*>(rec + rec_off_tiles(N, nb));
+    const int ntiles = nb * (nb + 1) / 2;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+
+    // ---------------------------------------------------------------- A. samples, gradflag, y
+    const float* smp = samples + (size_t)job.sample_off * w9;
+    // pass 1: flags per sample, warp-level compaction counts
+    for (int base = warp * 32; base < N; base += TRAIN_WARPS * 32) {
+        const int k = base + lane;
+        bool valid = false;
+        if (k < N) {
+            const float* s = smp + (size_t)k * w9;
+            const float sg = s[2 * dim + 2];
+            bool allsmall = true;
+            for (int c = 0; c < dim; ++c) allsmall = allsmall && (fabs((double)s[dim + c]) < 1e-6);
+            valid = !((double)sg > 0.1001 || allsmall);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) wtot[base >> 5] = __popc(m);
+    }
+    for (int i = tid; i < nb * 32; i += TRAIN_THREADS) { yv[i] = 0.f; }
+    __syncthreads();
+    // exclusive scan of the per-32 counts (N <= 1536 -> <= 48 chunks): done redundantly per thread
+    for (int base = warp * 32; base < N; base += TRAIN_WARPS * 32) {
+        const int k = base + lane;
+        int before = 0;
+        for (int c = 0; c < (base >> 5); ++c) before += wtot[c];
+        bool valid = false;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sx = 0.f, sg = 0.f, f = 0.f, g[3] = {0.f, 0.f, 0.f};
+        if (k < N) {
+            const float* s = smp + (size_t)k * w9;
+            p.x = s[0]; p.y = s[1]; p.z = (dim == 3) ? s[2] : 0.f;
+            for (int c = 0; c < dim; ++c) g[c] = s[dim + c];
+            f = s[2 * dim]; sx = s[2 * dim + 1]; sg = s[2 * dim + 2];
+            bool allsmall = true;
+            for (int c = 0; c < dim; ++c) allsmall = allsmall && (fabs((double)g[c]) < 1e-6);
+            valid = !((double)sg > 0.1001 || allsmall);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (k < N) {
+            int gi = -1;
+            if (valid) gi = before + __popc(m & ((1u << lane) - 1u));
+            else sx = 2.0f;  // OnGPIS.cpp:65,124
+            p.w = __int_as_float(gi);
+            pts[k] = p; sigx[k] = sx; sigg[k] = sg;
+            rec_pts[k] = p;
+            yv[k] = f;
+            if (gi >= 0)
+                for (int c = 0; c < dim; ++c) yv[N + c * ng + gi] = g[c];
+        }
+    }
+    // zero the tile array (padding rows/cols, structural zeros, strict upper parts)
+    {
+        float4* t4 = reinterpret_cast<float4*>(rec_tiles);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < ntiles * (GPIS_TILE_ELEMS / 4); i += TRAIN_THREADS) t4[i] = z4;
+    }
+    __syncthreads();
+    for (int i = tid; i < nb * 32; i += TRAIN_THREADS) zv[i] = yv[i];
+
+    // ---------------------------------------------------------------- B. covariance -> tiles
+    // Ordered pairs (a = row sample, b = column sample): an entry (row, col) of the lower triangle
+    // is written by exactly one pair, and lanes run along a so the stores are contiguous.
+#define KSTORE(row, col, v) rec_tiles[(size_t)tile_index((row) >> 5, (col) >> 5, nb) * GPIS_TILE_ELEMS + ((col) & 31) * 32 + ((row) & 31)] = (v)
+    {
+        // N <= 256: the thread block is split into `parts` groups that share the b loop; larger
+        // leaves give every thread several rows.
+        const int Npad = (N + 31) & ~31;
+        const int parts = max(1, TRAIN_THREADS / Npad);
+        const int a = (Npad >= TRAIN_THREADS) ? tid : tid % Npad;
+        const int part = (Npad >= TRAIN_THREADS) ? 0 : tid / Npad;
+        const int astride = (Npad >= TRAIN_THREADS) ? TRAIN_THREADS : (1 << 30);
+        for (int a0 = a; a0 < N && part < parts; a0 += astride) {
+            const float4 pa = pts[a0];
+            const int ga = __float_as_int(pa.w);
+            const float xa[3] = {pa.x, pa.y, pa.z};
+            for (int b = part; b < N; b += parts) {
+                if (b == a0) {
+                    KSTORE(a0, a0, (float)(1.0 + (double)sigx[a0]));  // covFnc.cpp:173
+                    if (ga >= 0) {
+                        for (int c = 0; c < dim; ++c) {
+                            const int rc = N + c * ng + ga;
+                            float v = P.a2 + sigg[a0];  // :182-190 / :355
+                            if (dim == 2 && c == 0) v = (float)((double)P.a2 + sqrt((double)(sigx[a0] * sigg[a0])));  // :352
+                            KSTORE(rc, rc, v);
+                        }
+                    }
+                    continue;
+                }
+                const float4 pb = pts[b];
+                const int gb = __float_as_int(pb.w);
+                if (ga < 0 && a0 < b) continue;  // nothing of this ordered pair lies in the lower triangle
+                const float xb[3] = {pb.x, pb.y, pb.z};
+                // orient differences like the reference: first index = smaller sample index
+                const bool fwd = a0 < b;
+                float d[3], s2 = 0.f;
+                for (int c = 0; c < dim; ++c) {
+                    d[c] = fwd ? (xa[c] - xb[c]) : (xb[c] - xa[c]);
+                    s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c];
+                }
+                const float r = sqrtf(s2);
+                const double e = exp((double)(-P.a * r));
+                // value(a) - value(b)
+                if (a0 > b) KSTORE(a0, b, kf_val(r, P.a, e));
+                if (ga >= 0) {
+                    // d/dc at a  vs  value at b:  -kf1(x_a - x_b)   (covFnc.cpp:198-203 / 239-249)
+                    for (int c = 0; c < dim; ++c) {
+                        const float k1 = kf1_val(d[c], P.a, e);   // kf1(x_first - x_second)
+                        KSTORE(N + c * ng + ga, b, fwd ? -k1 : k1);
+                    }
+                    if (gb >= 0) {
+                        for (int c = 0; c < dim; ++c)
+                            for (int e2 = 0; e2 < dim; ++e2) {
+                                const int row = N + c * ng + ga, col = N + e2 * ng + gb;
+                                if (row <= col) continue;
+                                const int c0 = min(c, e2), e0 = max(c, e2);
+                                KSTORE(row, col, kf2_val(r, d[c0], d[e0], c == e2 ? 1.f : 0.f, P.a, e));
+                            }
+                    }
+                }
+            }
+        }
+        // identity on the padded diagonal
+        for (int i = n + tid; i < nb * 32; i += TRAIN_THREADS) KSTORE(i, i, 1.0f);
+    }
+#undef KSTORE
+    __threadfence_block();
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---------------------------------------------------------------- C. blocked Cholesky + forward solve
+    int bad_total = 0;
+    uint32_t phase_bits = 0;  // parity of each stage barrier
+    for (int bj = 0; bj < nb; ++bj) {
+        const int ncol = nb - bj;  // tiles bi = bj .. nb-1
+        for (int g0 = 0; g0 < ncol; g0 += TRAIN_WARPS) {
+            const int gcount = min(TRAIN_WARPS, ncol - g0);
+            const int bi = bj + g0 + warp;
+            const bool have = warp < gcount;
+            float acc[4][8];
+            if (have) tile_load(rec_tiles + (size_t)tile_index(bi, bj, nb) * GPIS_TILE_ELEMS, acc, rg, cg);
+            // forward-solve rider: warp 0 of group 0 also keeps t_bj -= L(bj,bk) z_bk   (lane = row)
+            float tz = 0.f;
+            const bool rider = (g0 == 0 && warp == 0);
+            if (rider) tz = zv[bj * 32 + lane];
+
+            // pipeline over bk: stage s holds A tiles (bi, bk) for this group + B tile (bj, bk)
+            auto issue = [&](int bk, int s) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bars[s], (uint32_t)(gcount + 1) * GPIS_TILE_BYTES);
+                    // A tiles of the group are consecutive in the column-block-major array
+                    tma_load_1d(stage[s], rec_tiles + (size_t)tile_index(bj + g0, bk, nb) * GPIS_TILE_ELEMS,
+                                (uint32_t)gcount * GPIS_TILE_BYTES, &bars[s]);
+                    tma_load_1d(stage[s] + TRAIN_WARPS * GPIS_TILE_ELEMS,
+                                rec_tiles + (size_t)tile_index(bj, bk, nb) * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s]);
+                }
+            };
+            if (bj > 0) issue(0, 0 ^ 0);
+            for (int bk = 0; bk < bj; ++bk) {
+                const int s = bk & 1;
+                if (bk + 1 < bj) issue(bk + 1, s ^ 1);
+                mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+                phase_bits ^= (1u << s);
+                const float* B = stage[s] + TRAIN_WARPS * GPIS_TILE_ELEMS;
+                if (have) tile_mma_sub(acc, stage[s] + warp * GPIS_TILE_ELEMS, B, rg, cg);
+                if (rider) {
+                    float sdot = 0.f;
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) sdot = fmaf(B[k * 32 + lane], zv[bk * 32 + k], sdot);
+                    tz -= sdot;
+                }
+                __syncthreads();  // everyone is done with stage s before it is refilled
+            }
+
+            if (g0 == 0) {
+                // diagonal tile: factor + invert (warp 0 owns bi == bj)
+                if (warp == 0) {
+                    tile_store(scratch, acc, rg, cg);
+                    __syncwarp();
+                    bad_total += warp_chol_inv(scratch, dinv_s, lane);
+                    __syncwarp();
+                    // z_bj = inv(Ljj) t_bj
+                    zv[bj * 32 + lane] = tz;  // publish t (only this warp reads it back below)
+                    __syncwarp();
+                    float zr = 0.f;
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) zr = fmaf(dinv_s[k * 32 + lane], zv[bj * 32 + k], zr);
+                    __syncwarp();
+                    zv[bj * 32 + lane] = zr;
+                    // store L_jj and its inverse to the record
+                    float4* dstL = reinterpret_cast<float4*>(rec_tiles + (size_t)tile_index(bj, bj, nb) * GPIS_TILE_ELEMS);
+                    float4* dstD = reinterpret_cast<float4*>(rec_dinv + (size_t)bj * GPIS_TILE_ELEMS);
+                    const float4* srcL = reinterpret_cast<const float4*>(scratch);
+                    const float4* srcD = reinterpret_cast<const float4*>(dinv_s);
+                    for (int i = lane; i < GPIS_TILE_ELEMS / 4; i += 32) { dstL[i] = srcL[i]; dstD[i] = srcD[i]; }
+                }
+                __syncthreads();  // dinv_s and z_bj visible to every warp
+            }
+            if (have && !(g0 == 0 && warp == 0)) {
+                // X = acc * inv(Ljj)^T : X[r][c] = sum_k acc[r][k] Dinv[c][k]
+                tile_store(scratch, acc, rg, cg);
+                __syncwarp();
+                float x[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+                // B[k][c] = Dinv[c][k]: the k-major image of Dinv^T is Dinv read as (k, c) -> c*32 + k ...
+                // tile_mma_add wants B[k*32 + c]; Dinv is stored with element (row, col) at col*32+row,
+                // i.e. Dinv[c][k] sits at k*32 + c. That is exactly B[k*32 + c].
+                tile_mma_add(x, scratch, dinv_s, rg, cg);
+                tile_store(rec_tiles + (size_t)tile_index(bi, bj, nb) * GPIS_TILE_ELEMS, x, rg, cg);
+            }
+            __threadfence_block();
+            fence_proxy_async();
+            __syncthreads();  // scratch / dinv_s reuse, and tiles visible to the next TMA reads
+        }
+    }
+
+    // ---------------------------------------------------------------- D. backward solve L^T alpha = z
+    // alpha_j = inv(Ljj)^T ( z_j - sum_{i>j} L(i,j)^T alpha_i ), j = nb-1 .. 0. zv holds z; it is
+    // overwritten by alpha block by block. Warps split i; lane = column k of the tile.
+    float* part = reinterpret_cast<float*>(smem_raw + TrainSmem::off_scratch);  // TRAIN_WARPS x 32 partial sums
+    for (int bj = nb - 1; bj >= 0; --bj) {
+        float s = 0.f;
+        for (int bi = bj + 1 + warp; bi < nb; bi += TRAIN_WARPS) {
+            const float* T = rec_tiles + (size_t)tile_index(bi, bj, nb) * GPIS_TILE_ELEMS + lane * 32;  // column `lane`
+            const float* al = zv + bi * 32;
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) {
+                const float4 t = *reinterpret_cast<const float4*>(T + 4 * r4);
+                s = fmaf(t.x, al[4 * r4 + 0], s);
+                s = fmaf(t.y, al[4 * r4 + 1], s);
+                s = fmaf(t.z, al[4 * r4 + 2], s);
+                s = fmaf(t.w, al[4 * r4 + 3], s);
+            }
+        }
+        part[warp * 32 + lane] = s;
+        __syncthreads();
+        if (warp == 0) {
+            float t = zv[bj * 32 + lane];
+            for (int w = 0; w < TRAIN_WARPS; ++w) t -= part[w * 32 + lane];
+            // alpha_j[k] = sum_r Dinv[r][k] t[r]   (Dinv^T t); Dinv (r,k) at k*32 + r in the record
+            const float* D = rec_dinv + (size_t)bj * GPIS_TILE_ELEMS + lane * 32;
+            float acc1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) acc1 = fmaf(D[r], __shfl_sync(0xffffffffu, t, r), acc1);
+            zv[bj * 32 + lane] = acc1;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < nb * 32; i += TRAIN_THREADS) rec_alpha[i] = (i < n) ? zv[i] : 0.f;
+
+    // ---------------------------------------------------------------- E. query form of the factor
+    // Off-diagonal tiles are rewritten in place as G(i,j) = L(i,j) inv(Ljj): the query's block
+    // elimination then needs no per-block triangular solve on its dependency chain (query_v2.cuh).
+    // Diagonal tiles keep Ljj; inv(Ljj) stays in the dinv array.
+    for (int bj = 0; bj + 1 < nb; ++bj) {
+        // dinv_s <- row-major image of inv(Ljj): element (k, c) at k*32 + c
+        for (int i = tid; i < GPIS_TILE_ELEMS; i += TRAIN_THREADS) {
+            const int c = i >> 5, k = i & 31;                    // record: (row k, col c) at c*32 + k
+            dinv_s[k * 32 + c] = rec_dinv[(size_t)bj * GPIS_TILE_ELEMS + i];
+        }
+        __syncthreads();
+        for (int bi = bj + 1 + warp; bi < nb; bi += TRAIN_WARPS) {
+            float* Tg = rec_tiles + (size_t)tile_index(bi, bj, nb) * GPIS_TILE_ELEMS;
+            const float4* src = reinterpret_cast<const float4*>(Tg);
+            float4* dst = reinterpret_cast<float4*>(scratch);
+            for (int i = lane; i < GPIS_TILE_ELEMS / 4; i += 32) dst[i] = src[i];
+            __syncwarp();
+            float g[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[i][j] = 0.f;
+            tile_mma_add(g, scratch, dinv_s, rg, cg);
+            __syncwarp();
+            tile_store(Tg, g, rg, cg);
+        }
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        LeafHeader* h = reinterpret_cast<LeafHeader*>(rec);
+        h->N = N; h->ng = ng; h->n = n; h->nb = nb; h->dim = dim; h->chol_fail = bad_total; h->slot = job.slot;
+        h->bytes = rec_bytes(N, nb);
+        h->key = cell_key(job.cell[0], job.cell[1], dim == 3 ? job.cell[2] : 0);
+        for (int c = 0; c < 3; ++c) { h->cell[c] = job.cell[c]; h->centre[c] = job.centre[c]; }
+        h->cell[3] = 0; h->centre[3] = 0.f;
+        if (status) status[blockIdx.x] = bad_total;
+    }
+}
+
+}  // namespace gpis

@@ -1,0 +1,331 @@
+// K4, grouped evaluation: (query, leaf) pairs are bucketed by leaf, and one CTA solves up to
+// QB = 8 queries (32 right-hand sides) against one leaf, so a leaf's factor is streamed from
+// L2/HBM once per 8 queries instead of once per query.
+//
+// The record stores, for every off-diagonal tile, G(i,j) = L(i,j) * inv(L(j,j)) and, per block
+// row, Dinv(j) = inv(L(j,j)). With U = the right-hand sides after block elimination,
+//      U_i = B_i - sum_{j<i} G(i,j) U_j            (no per-block triangular solve on the chain)
+//      V_j = Dinv(j) U_j,  var = prior - sum V^2    (off the dependency chain)
+// which is algebraically L^{-1} B (OnGPIS.cpp:199-213) evaluated block-wise.
+//
+// Per CTA: U (npad x 32 floats) lives in shared memory for the whole solve; warp w owns block rows
+// i = w, w+8, ...; for block column j each warp pulls its G(i,j) tiles through its own
+// double-buffered TMA bulk-copy pipeline (4 KB tiles, mbarrier completion) and applies a 32x32x32
+// register-tiled FMA update. Bound: FP32 FMA pipe (2 n^2 MACs per query-evaluation); L2->SM
+// traffic is 4 n^2 / 8 bytes per evaluation.
+#pragma once
+#include <string>
+
+#include "common.cuh"
+#include "leaf_train.cuh"
+#include "query.cuh"
+
+namespace gpis {
+
+#define QB 8
+#define EVAL2_WARPS 8
+#define EVAL2_THREADS (EVAL2_WARPS * 32)
+
+struct SortBufs {
+    int32_t* count;    // nslots
+    int32_t* start;    // nslots + 1   (exclusive prefix of count)
+    int32_t* istart;   // nslots + 1   (exclusive prefix of ceil(count/QB))
+    int32_t* cursor;   // nslots
+    int2* sorted;      // npairs
+    int4* items;       // work items: slot, first sorted pair, count, unused
+    int32_t* totals;   // [0] = number of items
+};
+
+__global__ void k_pair_hist(const int2* __restrict__ pairs, int npairs, int32_t* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npairs) atomicAdd(&count[pairs[i].y & 0x0fffffff], 1);
+}
+
+// single-block exclusive scans over the slots
+__global__ void __launch_bounds__(1024) k_slot_scan(SortBufs S, int nslots) {
+    __shared__ int s_cnt[1024], s_itm[1024];
+    const int t = threadIdx.x;
+    const int per = (nslots + 1023) / 1024;
+    const int lo = t * per, hi = min(nslots, lo + per);
+    int c = 0, it = 0;
+    for (int i = lo; i < hi; ++i) { c += S.count[i]; it += (S.count[i] + QB - 1) / QB; }
+    s_cnt[t] = c; s_itm[t] = it;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int a = 0, b = 0;
+        if (t >= off) { a = s_cnt[t - off]; b = s_itm[t - off]; }
+        __syncthreads();
+        s_cnt[t] += a; s_itm[t] += b;
+        __syncthreads();
+    }
+    int pc = s_cnt[t] - c, pi = s_itm[t] - it;
+    for (int i = lo; i < hi; ++i) {
+        S.start[i] = pc; S.istart[i] = pi; S.cursor[i] = pc;
+        pc += S.count[i]; pi += (S.count[i] + QB - 1) / QB;
+    }
+    if (t == 1023) { S.start[nslots] = s_cnt[1023]; S.istart[nslots] = s_itm[1023]; S.totals[0] = s_itm[1023]; }
+}
+
+__global__ void k_pair_scatter(const int2* __restrict__ pairs, int npairs, SortBufs S) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const int2 p = pairs[i];
+    const int pos = atomicAdd(&S.cursor[p.y & 0x0fffffff], 1);
+    S.sorted[pos] = p;
+}
+
+__global__ void k_make_items(SortBufs S, int nslots) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const int c = S.count[s];
+    if (c == 0) return;
+    int it = S.istart[s];
+    for (int o = 0; o < c; o += QB) S.items[it++] = make_int4(s, S.start[s] + o, min(QB, c - o), 0);
+}
+
+struct Eval2Smem {
+    static constexpr int off_bar = 0;                                         // EVAL2_WARPS * 2 mbarriers
+    static constexpr int off_stage = 256;                                     // per warp 2 x 4 KB
+    static constexpr int off_red = off_stage + EVAL2_WARPS * 2 * GPIS_TILE_BYTES;  // 2 x 32 x EVAL2_WARPS floats
+    static constexpr int off_U = off_red + 2 * 32 * EVAL2_WARPS * 4;
+    static int total(int nbmax) { return off_U + nbmax * 32 * 32 * 4; }
+};
+
+// C[i][j] (4x8 per lane, rows 4rg.., cols 8cg..) of a row-major [32][32] smem tile
+__device__ __forceinline__ void ctile_load(const float* U, float (&acc)[4][8], int rg, int cg) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(U + (4 * rg + i) * 32 + 8 * cg);
+        const float4 b = *reinterpret_cast<const float4*>(U + (4 * rg + i) * 32 + 8 * cg + 4);
+        acc[i][0] = a.x; acc[i][1] = a.y; acc[i][2] = a.z; acc[i][3] = a.w;
+        acc[i][4] = b.x; acc[i][5] = b.y; acc[i][6] = b.z; acc[i][7] = b.w;
+    }
+}
+__device__ __forceinline__ void ctile_store(float* U, const float (&acc)[4][8], int rg, int cg) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<float4*>(U + (4 * rg + i) * 32 + 8 * cg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(U + (4 * rg + i) * 32 + 8 * cg + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+__global__ void __launch_bounds__(EVAL2_THREADS, 1)
+k_eval_v2(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, SortBufs S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int4 item = S.items[blockIdx.x];
+    const int slot = item.x, first = item.y, cnt = item.z;
+    const int dim = P.dim, w = 1 + dim;
+    const unsigned char* rec = reinterpret_cast<const unsigned char*>(T.rec[slot]);
+    const int4 meta = T.meta[slot];
+    const int N = meta.x, ng = meta.y, n = meta.z, nb = meta.w;
+    const int npad = nb * 32;
+    const float4* pts = reinterpret_cast<const float4*>(rec + rec_off_pts());
+    const float* alpha = reinterpret_cast<const float*>(rec + rec_off_alpha(N));
+    const float* dinv = reinterpret_cast<const float*>(rec + rec_off_dinv(N, nb));
+    const float* tiles = reinterpret_cast<const float*>(rec + rec_off_tiles(N, nb));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = lane >> 2, cg = lane & 3;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + Eval2Smem::off_bar) + warp * 2;
+    float* stg[2] = {reinterpret_cast<float*>(smem_raw + Eval2Smem::off_stage) + (warp * 2 + 0) * GPIS_TILE_ELEMS,
+                     reinterpret_cast<float*>(smem_raw + Eval2Smem::off_stage) + (warp * 2 + 1) * GPIS_TILE_ELEMS};
+    float* red = reinterpret_cast<float*>(smem_raw + Eval2Smem::off_red);   // [2][EVAL2_WARPS][32]
+    float* U = reinterpret_cast<float*>(smem_raw + Eval2Smem::off_U);       // [npad][32]
+
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+
+    // ---- right-hand sides: k* of every query of the item (covFnc.cpp:282-311 / 425-446)
+    {
+        float4* U4 = reinterpret_cast<float4*>(U);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < npad * 8; i += EVAL2_THREADS) U4[i] = z4;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * QB; idx += EVAL2_THREADS) {
+        const int qi = idx % QB, k = idx / QB;
+        if (qi >= cnt) continue;
+        const int q = S.sorted[first + qi].x;
+        float xq[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < dim; ++c) xq[c] = x[(int64_t)q * dim + c];
+        const float4 p = pts[k];
+        const int g = __float_as_int(p.w);
+        const float xs[3] = {p.x, p.y, p.z};
+        float d[3], s2 = 0.f;
+        for (int c = 0; c < dim; ++c) { d[c] = xs[c] - xq[c]; s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c]; }
+        const float r = sqrtf(s2);
+        const double e = exp((double)(-P.a * r));
+        float* col = U + 4 * qi;
+        col[k * 32] = kf_val(r, P.a, e);
+        float k1[3];
+        for (int c = 0; c < dim; ++c) { k1[c] = kf1_val(d[c], P.a, e); col[k * 32 + 1 + c] = k1[c]; }
+        if (g >= 0) {
+            for (int c = 0; c < dim; ++c) {
+                const int row = N + c * ng + g;
+                col[row * 32] = -k1[c];
+                for (int e2 = 0; e2 < dim; ++e2) {
+                    const int c0 = min(c, e2), e0 = max(c, e2);
+                    col[row * 32 + 1 + e2] = kf2_val(r, d[c0], d[e0], c == e2 ? 1.f : 0.f, P.a, e);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- mean: U^T alpha (OnGPIS.cpp:187); lane = column, warps split the rows
+    {
+        float mu = 0.f;
+        for (int i = warp; i < n; i += EVAL2_WARPS) mu = fmaf(U[i * 32 + lane], __ldg(alpha + i), mu);
+        red[warp * 32 + lane] = mu;
+        __syncthreads();
+        if (warp == 0) {
+            float s = 0.f;
+            for (int ww = 0; ww < EVAL2_WARPS; ++ww) s += red[ww * 32 + lane];
+            const int qi = lane >> 2, c = lane & 3;
+            if (qi < cnt && c < w) {
+                const int2 pr = S.sorted[first + qi];
+                W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + c] = s;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- block elimination: for column j, warp w updates its rows i > j, i = w (mod 8)
+    uint32_t ph = 0;  // parity bits of this warp's two barriers
+    for (int j = 0; j + 1 < nb; ++j) {
+        const float* Uj = U + j * 32 * 32;
+        int i0 = j + 1 + ((warp - (j + 1)) % EVAL2_WARPS + EVAL2_WARPS) % EVAL2_WARPS;  // first row >= j+1 owned by this warp
+        int s = 0;
+        if (i0 < nb && lane == 0) {
+            mbar_expect_tx(&bars[0], GPIS_TILE_BYTES);
+            tma_load_1d(stg[0], tiles + (size_t)tile_index(i0, j, nb) * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[0]);
+        }
+        for (int i = i0; i < nb; i += EVAL2_WARPS, s ^= 1) {
+            const int inext = i + EVAL2_WARPS;
+            if (inext < nb && lane == 0) {
+                mbar_expect_tx(&bars[s ^ 1], GPIS_TILE_BYTES);
+                tma_load_1d(stg[s ^ 1], tiles + (size_t)tile_index(inext, j, nb) * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s ^ 1]);
+            }
+            mbar_wait(&bars[s], (ph >> s) & 1u);
+            ph ^= (1u << s);
+            float acc[4][8];
+            float* Ui = U + i * 32 * 32;
+            ctile_load(Ui, acc, rg, cg);
+            tile_mma_sub(acc, stg[s], Uj, rg, cg);
+            ctile_store(Ui, acc, rg, cg);
+            __syncwarp();   // all lanes done reading stg[s] before it is refilled two iterations later
+        }
+        __syncthreads();    // U_{j+1} is final before anyone uses it as an operand
+    }
+
+    // ---- V_j = Dinv(j) U_j and the column sums of V^2 (OnGPIS.cpp:200-201)
+    float ss[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ss[c] = 0.f;
+    {
+        int s = 0;
+        const int j0 = warp;
+        if (j0 < nb && lane == 0) {
+            mbar_expect_tx(&bars[0], GPIS_TILE_BYTES);
+            tma_load_1d(stg[0], dinv + (size_t)j0 * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[0]);
+        }
+        for (int j = j0; j < nb; j += EVAL2_WARPS, s ^= 1) {
+            const int jn = j + EVAL2_WARPS;
+            if (jn < nb && lane == 0) {
+                mbar_expect_tx(&bars[s ^ 1], GPIS_TILE_BYTES);
+                tma_load_1d(stg[s ^ 1], dinv + (size_t)jn * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s ^ 1]);
+            }
+            mbar_wait(&bars[s], (ph >> s) & 1u);
+            ph ^= (1u << s);
+            float v[4][8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) v[a][b] = 0.f;
+            tile_mma_add(v, stg[s], U + j * 32 * 32, rg, cg);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) ss[b] = fmaf(v[a][b], v[a][b], ss[b]);
+            __syncwarp();
+        }
+    }
+    // reduce over the 8 row groups of the warp (lane bits 2..4), then over warps
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float t = ss[c];
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        ss[c] = t;
+    }
+    if (rg == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red[warp * 32 + 8 * cg + c] = ss[c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float s = 0.f;
+        for (int ww = 0; ww < EVAL2_WARPS; ++ww) s += red[ww * 32 + lane];
+        const int qi = lane >> 2, c = lane & 3;
+        if (qi < cnt && c < w) {
+            const int2 pr = S.sorted[first + qi];
+            const double prior = (c == 0) ? (double)P.prior_f : P.prior_g;   // OnGPIS.cpp:203-212 / 235-237
+            W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + w + c] = (float)(prior - (double)s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static inline int query_v2_init(std::string& err) {
+    cudaError_t e = cudaFuncSetAttribute(k_eval_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(k_eval_v2): ") + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
+// Buckets the npairs work items in W.pairs by leaf and evaluates them. *d_sort is a grow-only
+// device buffer owned by the context.
+static inline int query_v2_eval(cudaStream_t st, const float* d_x, const LeafTable& T, const QueryParams& P,
+                                const QueryWork& W, int npairs, int nslots, int max_nb, int32_t** d_sort,
+                                int64_t* sort_cap, int64_t* launches, std::string& err) {
+#define CK2(call)                                                                 \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return -2; } \
+    } while (0)
+    const int64_t max_items = npairs / QB + nslots + 1;
+    const int64_t need = (int64_t)nslots * 4 + 8 + (int64_t)npairs * 2 + max_items * 4 + 64;
+    if (*sort_cap < need) {
+        if (*d_sort) CK2(cudaFree(*d_sort));
+        *d_sort = nullptr; *sort_cap = 0;
+        CK2(cudaMalloc(d_sort, sizeof(int32_t) * (need + need / 4)));
+        *sort_cap = need + need / 4;
+    }
+    SortBufs S;
+    int32_t* p = *d_sort;
+    S.totals = p; p += 16;
+    S.count = p; p += nslots;
+    S.start = p; p += nslots + 1;
+    S.istart = p; p += nslots + 1;
+    S.cursor = p; p += nslots;
+    p += ((uintptr_t)p & 15) ? (4 - (((uintptr_t)p >> 2) & 3)) : 0;   // 16-byte align for int4
+    S.items = reinterpret_cast<int4*>(p); p += max_items * 4;
+    S.sorted = reinterpret_cast<int2*>(p);
+    CK2(cudaMemsetAsync(S.count, 0, sizeof(int32_t) * nslots, st));
+    k_pair_hist<<<(npairs + 255) / 256, 256, 0, st>>>(W.pairs, npairs, S.count);
+    k_slot_scan<<<1, 1024, 0, st>>>(S, nslots);
+    k_pair_scatter<<<(npairs + 255) / 256, 256, 0, st>>>(W.pairs, npairs, S);
+    k_make_items<<<(nslots + 255) / 256, 256, 0, st>>>(S, nslots);
+    *launches += 4;
+    int32_t nitems = 0;
+    CK2(cudaMemcpyAsync(&nitems, S.totals, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK2(cudaStreamSynchronize(st));
+    if (nitems > 0) {
+        k_eval_v2<<<nitems, EVAL2_THREADS, Eval2Smem::total(max_nb), st>>>(d_x, T, P, W, S);
+        *launches += 1;
+        CK2(cudaGetLastError());
+    }
+#undef CK2
+    return 0;
+}
+
+}  // namespace gpis

@@ -1,0 +1,363 @@
+// Host-side point-region tree (quadtree for D = 2, octree for D = 3) that decides leaf assignment.
+//
+// Behavioural contract = the reference's QuadTree / OcTree (cpp/src/quadtree.cpp, cpp/src/octree.cpp,
+// cpp/include/octree.h, cpp/include/quadtree.h): same strict containsPoint / inclusive
+// intersectsAABB float tests, same child visiting order (NW,NE,SW,SE[,then the back four]), same
+// subdivision / minimum spacing / root growth rules, so that sample-to-leaf assignment, training
+// set order (QueryRange DFS order = row order of K) and candidate lists stay bit-exact. The
+// implementation is new: one template for both dimensions, nodes in an index-linked arena with
+// children allocated as one block, samples in a pool, no per-node heap objects or shared_ptr.
+//
+// This is bookkeeping around the GPU hot path (SURVEY.md §8a "adjacent but not on the GPU path").
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace gpismap_host {
+
+template <int D>
+struct Sample {
+    float pos[D];
+    float grad[D];
+    float val = 0.f, pose_sig = 0.f, grad_sig = 0.f;   // defaults = Node3(Point3) ctor (strct.cpp:72-79)
+    Sample() { for (int c = 0; c < D; ++c) { pos[c] = 0.f; grad[c] = 0.f; } }
+};
+
+struct TreeParam {           // cpp/include/strct.h:175-199
+    float initroot_half, min_half, min_half_sqr, max_half, cluster_half;
+    float reg_tol_insert;    // cluster registration tolerance on insert: 1e-6 (octree.cpp:325) / 1e-3 (quadtree.cpp:262)
+    bool reg_at_maxdepth;    // quadtree.cpp:240-241 registers at max depth, octree.cpp:305-313 does not
+    TreeParam(float mi, float ma, float ini, float c, float tol, bool rmd)
+        : initroot_half(ini), min_half(mi), min_half_sqr(mi * mi), max_half(ma), cluster_half(c),
+          reg_tol_insert(tol), reg_at_maxdepth(rmd) {}
+};
+
+template <int D>
+class PRTree {
+public:
+    static constexpr int NCH = 1 << D;
+    struct Cell {
+        float c[D];
+        float half;
+        float lo[D], hi[D];      // c - half, c + half in float (AABB ctor, octree.h:73-78)
+        int32_t parent = -1;
+        int32_t child0 = -1;     // first of NCH consecutive children, -1 = leaf
+        int32_t sample = -1;
+        int32_t count = 0;       // numNodes
+        uint32_t gen = 0;        // bumped when the cell is freed (stale-handle detection)
+        bool max_depth = false, root_limit = false, alive = true;
+    };
+
+    explicit PRTree(const TreeParam& p) : P(p) {
+        float c0[D];
+        for (int a = 0; a < D; ++a) c0[a] = 0.f;     // GPisMap3.cpp:574, GPisMap.cpp:460: rooted at the origin
+        root_ = new_cell(c0, P.initroot_half, -1, /*derive_flags=*/false);
+    }
+
+    int root() const { return root_; }
+    const Cell& cell(int i) const { return cells_[i]; }
+    const Sample<D>& sample(int s) const { return samples_[s]; }
+    Sample<D>& sample(int s) { return samples_[s]; }
+    bool cell_alive(int i, uint32_t gen) const { return i >= 0 && i < (int)cells_.size() && cells_[i].alive && cells_[i].gen == gen; }
+    bool is_cluster_level(int i) const { return std::fabs((double)cells_[i].half - (double)P.cluster_half) < 1e-3; }
+    bool is_empty_leaf(int i) const { return cells_[i].child0 < 0 && cells_[i].sample < 0; }
+    const TreeParam& param() const { return P; }
+
+    int new_sample(const float* pos) {
+        Sample<D> s;
+        for (int a = 0; a < D; ++a) s.pos[a] = pos[a];
+        samples_.push_back(s);
+        return (int)samples_.size() - 1;
+    }
+
+    // ---- IsNotNew (octree.cpp:431-458)
+    bool is_not_new(const float* p) const { return is_not_new(root_, p); }
+
+    // ---- Insert(n, quads) from the root (octree.cpp:295-414 / quadtree.cpp:223-312); follows root
+    // growth (t = t->getRoot(), GPisMap3.cpp:615-618). `touched` receives the cluster-level cells the
+    // insertion registered (vecInserted).
+    bool insert(int s, std::vector<int>& touched) {
+        const bool ok = insert_rec(root_, s, &touched);
+        while (cells_[root_].parent >= 0) root_ = cells_[root_].parent;
+        return ok;
+    }
+
+    // ---- Remove(n, set) (octree.cpp:510-566); cells deleted by a collapse are reported in `freed`
+    // (the reference erases them from the active set).
+    bool remove_tracked(int s, std::vector<int>& freed) { return remove_rec(root_, samples_[s].pos, true, &freed); }
+    // ---- Remove(n) (octree.cpp:460-508): visits every child, collapses, reports freed cells too
+    bool remove_plain(int s, std::vector<int>& freed) { return remove_rec(root_, samples_[s].pos, false, &freed); }
+
+    // ---- QueryRange (octree.cpp:777-804): samples with |p - c|^2 < (half)^2, DFS order
+    void query_range(const float* c, float half, std::vector<int>& out) const {
+        float lo[D], hi[D];
+        for (int a = 0; a < D; ++a) { lo[a] = c[a] - half; hi[a] = c[a] + half; }
+        query_range_rec(root_, c, half * half, lo, hi, out);
+    }
+
+    // ---- QueryNonEmptyLevelC (octree.cpp:829-893): non-empty cluster-level cells hitting the box
+    void query_clusters(const float* c, float half, std::vector<int>& out) const {
+        float lo[D], hi[D];
+        for (int a = 0; a < D; ++a) { lo[a] = c[a] - half; hi[a] = c[a] + half; }
+        query_clusters_rec(root_, lo, hi, out);
+    }
+
+    // ---- getAllChildrenNonEmptyNodes (octree.cpp:806-827)
+    void collect_samples(int cell_id, std::vector<int>& out) const {
+        const Cell& n = cells_[cell_id];
+        if (n.child0 < 0) { if (n.sample >= 0) out.push_back(n.sample); return; }
+        for (int k = 0; k < NCH; ++k) collect_samples(n.child0 + k, out);
+    }
+
+    // Intersection of the float boxes of a cell and all its ancestors: what the level-by-level pruning
+    // of QueryNonEmptyLevelC (octree.cpp:864-867) lets through.
+    void effective_box(int cell_id, float* lo, float* hi) const {
+        for (int a = 0; a < D; ++a) { lo[a] = cells_[cell_id].lo[a]; hi[a] = cells_[cell_id].hi[a]; }
+        for (int p = cells_[cell_id].parent; p >= 0; p = cells_[p].parent)
+            for (int a = 0; a < D; ++a) { lo[a] = std::max(lo[a], cells_[p].lo[a]); hi[a] = std::min(hi[a], cells_[p].hi[a]); }
+    }
+
+    size_t num_cells() const { return cells_.size(); }
+    size_t num_samples() const { return samples_.size(); }
+
+private:
+    TreeParam P;
+    std::vector<Cell> cells_;
+    std::vector<Sample<D>> samples_;
+    std::vector<int32_t> free_blocks_;   // recycled child blocks
+    int root_ = -1;
+
+    static float sqdist(const float* a, const float* b) {   // octree.cpp:24-31
+        float s = 0.f;
+        for (int c = 0; c < D; ++c) { const float d = a[c] - b[c]; s = (c == 0) ? d * d : s + d * d; }
+        return s;
+    }
+    // child k of the reference's visiting order: bit0 = east (+x); bit1 = south (-y); bit2 = back (-z)
+    static float child_sign(int k, int axis) {
+        if (axis == 0) return (k & 1) ? 1.f : -1.f;
+        return ((k >> axis) & 1) ? -1.f : 1.f;
+    }
+    void init_cell(Cell& n, const float* c, float half, int parent, bool derive_flags) {
+        for (int a = 0; a < D; ++a) { n.c[a] = c[a]; n.lo[a] = c[a] - half; n.hi[a] = c[a] + half; }
+        n.half = half; n.parent = parent; n.child0 = -1; n.sample = -1; n.count = 0; n.alive = true;
+        n.max_depth = derive_flags && (half < P.min_half);     // octree.cpp:72-75
+        n.root_limit = derive_flags && (half > P.max_half);
+    }
+    int new_cell(const float* c, float half, int parent, bool derive_flags) {
+        cells_.emplace_back();
+        init_cell(cells_.back(), c, half, parent, derive_flags);
+        return (int)cells_.size() - 1;
+    }
+    int alloc_children() {
+        if (!free_blocks_.empty()) { const int b = free_blocks_.back(); free_blocks_.pop_back(); return b; }
+        const int b = (int)cells_.size();
+        cells_.resize(cells_.size() + NCH);
+        return b;
+    }
+    bool contains(const Cell& n, const float* p) const {    // strict, octree.h:119-126
+        for (int a = 0; a < D; ++a) if (!(p[a] > n.lo[a] && p[a] < n.hi[a])) return false;
+        return true;
+    }
+    static bool intersects(const Cell& n, const float* lo, const float* hi) {   // inclusive, octree.h:128-135
+        for (int a = 0; a < D; ++a) if (hi[a] < n.lo[a] || lo[a] > n.hi[a]) return false;
+        return true;
+    }
+    // Subdivide (octree.cpp:672-713): children at c +- half/2, visiting order as above
+    void subdivide(int id, int except_k = -1, int except_cell = -1) {
+        const int b = alloc_children();
+        const float l = (float)((double)cells_[id].half * 0.5);
+        for (int k = 0; k < NCH; ++k) {
+            float c[D];
+            for (int a = 0; a < D; ++a) c[a] = cells_[id].c[a] + child_sign(k, a) * l;
+            Cell& ch = cells_[b + k];
+            const uint32_t g = ch.gen;
+            init_cell(ch, c, l, id, true);
+            ch.gen = g;
+        }
+        cells_[id].child0 = b;
+        (void)except_k; (void)except_cell;
+    }
+    void update_count(int id) {
+        Cell& n = cells_[id];
+        if (n.child0 < 0) return;
+        int s = 0;
+        for (int k = 0; k < NCH; ++k) s += cells_[n.child0 + k].count;
+        n.count = s;
+    }
+    bool reg_ok(const Cell& n) const { return std::fabs((double)n.half - (double)P.cluster_half) < (double)P.reg_tol_insert; }
+
+    // InsertToParent (octree.cpp:151-212): the root grows toward the point; the old root becomes
+    // the child diagonally opposite, and the insertion continues WITHOUT cluster registration
+    // (it calls the overload that takes no set).
+    bool insert_to_parent(int id, int s) {
+        const float* np = samples_[s].pos;
+        const float l = cells_[id].half;
+        float pc[D];
+        for (int a = 0; a < D; ++a) pc[a] = 0.f;     // Point3<float> par_c default-constructs to 0
+        int child_k = -1;
+        // the chain of ifs in the reference requires a strict inequality on every axis
+        bool strict = true;
+        for (int a = 0; a < D; ++a) if (!(np[a] < cells_[id].c[a] || np[a] > cells_[id].c[a])) strict = false;
+        if (strict) {
+            child_k = 0;
+            for (int a = 0; a < D; ++a) {
+                const bool up = np[a] > cells_[id].c[a];
+                pc[a] = up ? cells_[id].c[a] + l : cells_[id].c[a] - l;
+                // the old root sits on the side away from the point: sign = up ? -1 : +1
+                const float sgn = up ? -1.f : 1.f;
+                if (a == 0) { if (sgn > 0) child_k |= 1; }
+                else { if (sgn < 0) child_k |= (1 << a); }
+            }
+        }
+        const float ph = (float)(2.0 * (double)l);
+        const int par = new_cell(pc, ph, -1, true);
+        if (child_k >= 0) {
+            // SubdivideExcept (octree.cpp:715-775): allocate the block, then let the old root take
+            // the place of child_k. Arena children must be contiguous, so the old root's contents
+            // are moved into the block slot and every reference to it is re-pointed.
+            const int b = alloc_children();
+            const float hl = (float)((double)ph * 0.5);
+            for (int k = 0; k < NCH; ++k) {
+                if (k == child_k) continue;
+                float c[D];
+                for (int a = 0; a < D; ++a) c[a] = pc[a] + child_sign(k, a) * hl;
+                Cell& ch = cells_[b + k];
+                const uint32_t g = ch.gen;
+                init_cell(ch, c, hl, par, true);
+                ch.gen = g;
+            }
+            move_cell(id, b + child_k);
+            cells_[b + child_k].parent = par;
+            cells_[par].child0 = b;
+        }
+        // child_k < 0: a point exactly on one of the root's centre planes. The reference then builds
+        // a fresh childless parent at the origin and the old subtree is orphaned (octree.cpp:96-99).
+        if (child_k < 0) { cells_[id].parent = par; orphaned_ = true; }
+        root_ = par;
+        return insert_rec(par, s, nullptr);
+    }
+    // move cell `from` (with its subtree links) to slot `to`
+    void move_cell(int from, int to) {
+        const uint32_t g = cells_[to].gen;
+        cells_[to] = cells_[from];
+        cells_[to].gen = g;
+        if (cells_[to].child0 >= 0)
+            for (int k = 0; k < NCH; ++k) cells_[cells_[to].child0 + k].parent = to;
+        cells_[from].alive = false;
+        cells_[from].gen++;
+        cells_[from].child0 = -1; cells_[from].sample = -1;
+        moved_from_ = from; moved_to_ = to;
+    }
+
+    bool insert_rec(int id, int s, std::vector<int>* quads) {
+        const float* p = samples_[s].pos;
+        if (!contains(cells_[id], p)) {
+            if (cells_[id].parent < 0) {
+                if (cells_[id].root_limit) return false;
+                return insert_to_parent(id, s);
+            }
+            return false;
+        }
+        if (cells_[id].max_depth) {
+            if (cells_[id].sample < 0) {
+                cells_[id].sample = s; cells_[id].count = 1;
+                if (quads && P.reg_at_maxdepth && reg_ok(cells_[id])) quads->push_back(id);
+                return true;
+            }
+            return false;
+        }
+        if (cells_[id].child0 < 0) {
+            if (cells_[id].half > P.cluster_half) {
+                subdivide(id);
+            } else {
+                if (cells_[id].sample < 0) {
+                    cells_[id].sample = s; cells_[id].count = 1;
+                    if (quads && reg_ok(cells_[id])) quads->push_back(id);
+                    return true;
+                }
+                if (sqdist(samples_[cells_[id].sample].pos, p) < P.min_half_sqr) return false;
+                const int old = cells_[id].sample;
+                subdivide(id);
+                for (int k = 0; k < NCH; ++k)
+                    if (insert_rec(cells_[id].child0 + k, old, quads)) break;
+                cells_[id].sample = -1;   // dropped silently if no child took it (lattice-plane rejection)
+            }
+        }
+        for (int k = 0; k < NCH; ++k) {
+            if (insert_rec(cells_[id].child0 + k, s, quads)) {
+                if (quads && reg_ok(cells_[id])) quads->push_back(id);
+                update_count(id);
+                return true;
+            }
+        }
+        return false;
+    }
+
+    bool is_not_new(int id, const float* p) const {
+        const Cell& n = cells_[id];
+        if (!contains(n, p)) return false;
+        if (n.child0 < 0 && n.sample < 0) return false;
+        if (n.sample >= 0 && sqdist(samples_[n.sample].pos, p) < P.min_half_sqr) return true;
+        if (n.child0 < 0) return false;
+        for (int k = 0; k < NCH; ++k) if (is_not_new(n.child0 + k, p)) return true;
+        return false;
+    }
+
+    bool remove_rec(int id, const float* p, bool short_circuit, std::vector<int>* freed) {
+        if (!contains(cells_[id], p)) return false;
+        if (is_empty_leaf(id)) return false;
+        if (cells_[id].sample >= 0 && (double)sqdist(samples_[cells_[id].sample].pos, p) < 1e-12) {   // EPS, octree.cpp:22
+            cells_[id].sample = -1; cells_[id].count = 0;
+            return true;
+        }
+        if (cells_[id].child0 < 0) return false;
+        bool res = false;
+        for (int k = 0; k < NCH; ++k) {
+            if (short_circuit && res) break;
+            res = remove_rec(cells_[id].child0 + k, p, short_circuit, freed) || res;
+        }
+        if (res) {
+            bool all_empty = true;
+            for (int k = 0; k < NCH; ++k) all_empty = all_empty && is_empty_leaf(cells_[id].child0 + k);
+            if (all_empty) {
+                const int b = cells_[id].child0;
+                for (int k = 0; k < NCH; ++k) {
+                    if (freed) freed->push_back(b + k);
+                    cells_[b + k].alive = false;
+                    cells_[b + k].gen++;
+                }
+                free_blocks_.push_back(b);
+                cells_[id].child0 = -1;
+                cells_[id].count = 0;
+            }
+        }
+        update_count(id);
+        return res;
+    }
+
+    void query_range_rec(int id, const float* c, float r2, const float* lo, const float* hi, std::vector<int>& out) const {
+        const Cell& n = cells_[id];
+        if (!intersects(n, lo, hi) || (n.child0 < 0 && n.sample < 0)) return;
+        if (n.child0 < 0) {
+            if (sqdist(samples_[n.sample].pos, c) < r2) out.push_back(n.sample);
+            return;
+        }
+        for (int k = 0; k < NCH; ++k) query_range_rec(n.child0 + k, c, r2, lo, hi, out);
+    }
+    void query_clusters_rec(int id, const float* lo, const float* hi, std::vector<int>& out) const {
+        const Cell& n = cells_[id];
+        if (!intersects(n, lo, hi) || (n.child0 < 0 && n.sample < 0)) return;
+        const bool above = (double)n.half > (double)P.cluster_half + 0.001;
+        if (n.child0 < 0 && above) return;
+        if (above) { for (int k = 0; k < NCH; ++k) query_clusters_rec(n.child0 + k, lo, hi, out); }
+        else out.push_back(id);
+    }
+
+public:
+    bool orphaned_ = false;
+    int moved_from_ = -1, moved_to_ = -1;   // last root relocation (insert_to_parent), for handle fix-up
+};
+
+}  // namespace gpismap_host

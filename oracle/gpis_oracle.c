@@ -285,12 +285,13 @@ void gpo_gp_test(const gpo_gp* g, const real* x, int m, real* res) {
 struct gpo_map {
     int dim, nc;
     float* centres; /* nc x dim */
+    float* boxes;   /* nc x 2*dim: effective lo, hi */
     float half, search_half;
     real var_thre, noise;
     gpo_gp** gps;
 };
 gpo_map* gpo_map_create(int dim, int nclusters, const float* centres, float cluster_half, gpo_gp* const* gps,
-                        float search_half, float var_thre, float noise) {
+                        float search_half, float var_thre, float noise, const float* boxes) {
     gpo_map* m = (gpo_map*)calloc(1, sizeof(gpo_map));
     m->dim = dim; m->nc = nclusters; m->half = cluster_half; m->search_half = search_half;
     m->var_thre = (real)var_thre; m->noise = (real)noise;
@@ -298,11 +299,80 @@ gpo_map* gpo_map_create(int dim, int nclusters, const float* centres, float clus
     memcpy(m->centres, centres, sizeof(float) * (size_t)nclusters * dim);
     m->gps = (gpo_gp**)malloc(sizeof(gpo_gp*) * (nclusters > 0 ? nclusters : 1));
     memcpy(m->gps, gps, sizeof(gpo_gp*) * nclusters);
+    m->boxes = (float*)malloc(sizeof(float) * (size_t)(nclusters > 0 ? nclusters : 1) * 2 * dim);
+    for (int i = 0; i < nclusters; ++i)
+        for (int c = 0; c < dim; ++c) {
+            m->boxes[(size_t)i * 2 * dim + c] = boxes ? boxes[(size_t)i * 2 * dim + c] : centres[(size_t)i * dim + c] - cluster_half;
+            m->boxes[(size_t)i * 2 * dim + dim + c] = boxes ? boxes[(size_t)i * 2 * dim + dim + c] : centres[(size_t)i * dim + c] + cluster_half;
+        }
     return m;
 }
 void gpo_map_free(gpo_map* m) {
     if (!m) return;
-    free(m->centres); free(m->gps); free(m);
+    free(m->centres); free(m->boxes); free(m->gps); free(m);
+}
+
+/* ------------------------------------------------------------------ libstdc++ std::sort replay
+ * bits/stl_algo.h (GCC 13): __sort -> __introsort_loop (median-of-3 to first, unguarded partition,
+ * threshold 16, depth limit 2*floor(log2 n), heapsort fallback) -> __final_insertion_sort.
+ * Sorts the parallel arrays (idx, key) by key with comparator key[a] < key[b]; the arrays start in
+ * the tree's DFS order. The heapsort fallback needs > 2 log2(n) bad partitions and does not occur
+ * for n <= 256 candidate lists; if it ever did, the remaining range is finished by insertion. */
+static void ssr_swap(int* idx, float* key, int a, int b) {
+    int ti = idx[a]; idx[a] = idx[b]; idx[b] = ti;
+    float tk = key[a]; key[a] = key[b]; key[b] = tk;
+}
+static void ssr_unguarded_linear_insert(int* idx, float* key, int last) {
+    const int vi = idx[last]; const float vk = key[last];
+    int next = last - 1;
+    while (vk < key[next]) { idx[last] = idx[next]; key[last] = key[next]; last = next; --next; }
+    idx[last] = vi; key[last] = vk;
+}
+static void ssr_insertion_sort(int* idx, float* key, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (key[i] < key[first]) {
+            const int vi = idx[i]; const float vk = key[i];
+            for (int j = i; j > first; --j) { idx[j] = idx[j - 1]; key[j] = key[j - 1]; }
+            idx[first] = vi; key[first] = vk;
+        } else ssr_unguarded_linear_insert(idx, key, i);
+    }
+}
+static void ssr_introsort_loop(int* idx, float* key, int first, int last, int depth) {
+    while (last - first > 16) {
+        if (depth == 0) { ssr_insertion_sort(idx, key, first, last); return; }
+        --depth;
+        /* __move_median_to_first(first, first+1, mid, last-1) */
+        const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+        int med;
+        if (key[a] < key[b]) { if (key[b] < key[c]) med = b; else if (key[a] < key[c]) med = c; else med = a; }
+        else if (key[a] < key[c]) med = a;
+        else if (key[b] < key[c]) med = c;
+        else med = b;
+        ssr_swap(idx, key, first, med);
+        /* __unguarded_partition(first+1, last, pivot = first) */
+        int lo = first + 1, hi = last;
+        for (;;) {
+            while (key[lo] < key[first]) ++lo;
+            --hi;
+            while (key[first] < key[hi]) --hi;
+            if (!(lo < hi)) break;
+            ssr_swap(idx, key, lo, hi);
+            ++lo;
+        }
+        ssr_introsort_loop(idx, key, lo, last, depth);
+        last = lo;
+    }
+}
+static void std_sort_replay(int* idx, float* key, int n) {
+    if (n <= 1) return;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    ssr_introsort_loop(idx, key, 0, n, 2 * lg);
+    if (n > 16) {
+        ssr_insertion_sort(idx, key, 0, 16);
+        for (int i = 16; i != n; ++i) ssr_unguarded_linear_insert(idx, key, i);
+    } else ssr_insertion_sort(idx, key, 0, n);
 }
 
 /* One query: GPisMap3.cpp:803-900 / GPisMap.cpp:673-761. Geometry is always fp32 (it decides
@@ -318,7 +388,7 @@ static void map_test_point(const gpo_map* m, const float* x, real* res, int* cho
         const float* ct = m->centres + (size_t)i * dim;
         int hit = 1;
         for (int c = 0; c < dim; ++c) {
-            const float lo = ct[c] - m->half, hi = ct[c] + m->half;
+            const float lo = m->boxes[(size_t)i * 2 * dim + c], hi = m->boxes[(size_t)i * 2 * dim + dim + c];
             if (qhi[c] < lo || qlo[c] > hi) { hit = 0; break; }
         }
         if (!hit) continue;
@@ -326,13 +396,10 @@ static void map_test_point(const gpo_map* m, const float* x, real* res, int* cho
         for (int c = 0; c < dim; ++c) { float d = ct[c] - x[c]; s = c == 0 ? d * d : s + d * d; }
         idx[nc] = i; sq[nc] = s; ++nc;
     }
-    /* stable insertion sort by distance == std::sort for <= 16 elements; for more the
-     * reference's introsort may order exact ties differently: flagged. */
-    for (int i = 1; i < nc; ++i) {
-        int ii = idx[i]; float si = sq[i]; int j = i - 1;
-        while (j >= 0 && sq[j] > si) { idx[j + 1] = idx[j]; sq[j + 1] = sq[j]; --j; }
-        idx[j + 1] = ii; sq[j + 1] = si;
-    }
+    /* std::sort over the index array with comparator sqdst[i1] < sqdst[i2] (GPisMap3.cpp:826-829):
+     * replayed exactly (libstdc++ introsort), because for more than 16 candidates exact distance
+     * ties are ordered by the partitioning, not by DFS order. */
+    std_sort_replay(idx, sq, nc);
     const int numc = nc > 3 ? 3 : nc;
     if (chosen) {
         chosen[0] = nc;
@@ -441,6 +508,7 @@ struct gpo_obs {
     int d;          /* 1 or 2 */
     int ng0, ng1;   /* tile grid (ng1 = 1 in 1-D) */
     int nb0, nb1;   /* boundary counts */
+    int ni, nj;     /* grid the partition was computed for */
     float* b0;      /* Val_i / range */
     float* b1;      /* Val_j */
     gpou** gps;
@@ -455,7 +523,14 @@ struct gpo_obs {
 #define OBS_MARGIN1 0.0175f
 
 /* ObsGP.cpp:204-265 (partition) + 280-329 (training of tiles with >= 1 valid pixel) */
+gpo_obs* gpo_obs2d_retrain(const float* vu, const float* zinv, int ni, int nj, const gpo_obs* prev);
 gpo_obs* gpo_obs2d_train(const float* vu, const float* zinv, int ni, int nj) {
+    return gpo_obs2d_retrain(vu, zinv, ni, nj, NULL);
+}
+/* prev: the previous frame's regressor. ObsGP2D keeps its partition boundaries (Val_i / Val_j)
+ * while the grid dimensions stay the same (ObsGP.cpp:335-337; regressObs calls the non-virtual base
+ * reset(), GPisMap3.cpp:252), even if the pixel coordinates changed (resetCam). */
+gpo_obs* gpo_obs2d_retrain(const float* vu, const float* zinv, int ni, int nj, const gpo_obs* prev) {
     if (ni <= 0 || nj <= 0 || !vu) return NULL;
     gpo_obs* o = (gpo_obs*)calloc(1, sizeof(gpo_obs));
     o->d = 2; o->margin = OBS_MARGIN2;
@@ -481,6 +556,11 @@ gpo_obs* gpo_obs2d_train(const float* vu, const float* zinv, int ni, int nj) {
         else { j1[m] = nj - 1; o->b1[m + 1] = vu[2 * j1[m] * ni + 1]; }
     }
     o->nb0 = o->ng0 + 1; o->nb1 = o->ng1 + 1;
+    if (prev && prev->d == 2 && prev->ng0 == o->ng0 && prev->ng1 == o->ng1 && prev->ni == ni && prev->nj == nj) {
+        memcpy(o->b0, prev->b0, sizeof(float) * o->nb0);
+        memcpy(o->b1, prev->b1, sizeof(float) * o->nb1);
+    }
+    o->ni = ni; o->nj = nj;
     o->ngps = o->ng0 * o->ng1;
     o->gps = (gpou**)calloc(o->ngps > 0 ? o->ngps : 1, sizeof(gpou*));
     const int cap = (g + ov + 8) * (g + ov + 8) + ni + nj;

@@ -56,8 +56,13 @@ void gpo_gp_test(const gpo_gp* g, const real* x, int m, real* res);
  * The map is a list of non-empty clusters in the tree's DFS order. gps[i] may be NULL
  * (non-empty but never trained). */
 typedef struct gpo_map gpo_map;
+/* boxes (optional, nclusters x 2*dim floats: lo[dim], hi[dim]): the effective box of each cluster =
+ * intersection of its own float AABB with those of all its tree ancestors. The reference prunes
+ * its DFS at every level with float boxes (octree.cpp:864-867), and c-l / c+l of a parent can round
+ * past its child's, so a query box that only touches a lattice plane can be cut off above the
+ * cluster level. NULL = own box only (centre -/+ cluster_half). */
 gpo_map* gpo_map_create(int dim, int nclusters, const float* centres, float cluster_half, gpo_gp* const* gps,
-                        float search_half, float var_thre, float noise);
+                        float search_half, float var_thre, float noise, const float* boxes);
 void gpo_map_free(gpo_map* m);
 /* res: m rows of 2(1+dim), in/out (fields the logic does not reach stay untouched).
  * chosen (optional): m x 4 ints = [ncandidates, id0, id1, id2] (ids index the cluster list,
@@ -69,6 +74,7 @@ void gpo_map_test(const gpo_map* m, const float* x, int n, real* res, int* chose
  * 85-187 (ObsGP1D). */
 typedef struct gpo_obs gpo_obs;
 gpo_obs* gpo_obs2d_train(const float* vu, const float* zinv, int ni, int nj);
+gpo_obs* gpo_obs2d_retrain(const float* vu, const float* zinv, int ni, int nj, const gpo_obs* prev);
 gpo_obs* gpo_obs1d_train(const float* theta, const float* f, int n);
 void gpo_obs_free(gpo_obs* o);
 int gpo_obs_ntiles(const gpo_obs* o);

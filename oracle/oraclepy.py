@@ -44,7 +44,7 @@ class Oracle:
             "gpo_gp_chol_fail": (C.c_int, [vp]),
             "gpo_gp_get": (None, [vp, vp, vp, vp]),
             "gpo_gp_test": (None, [vp, rp, C.c_int, rp]),
-            "gpo_map_create": (vp, [C.c_int, C.c_int, fp, C.c_float, vp, C.c_float, C.c_float, C.c_float]),
+            "gpo_map_create": (vp, [C.c_int, C.c_int, fp, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp]),
             "gpo_map_free": (None, [vp]),
             "gpo_map_test": (None, [vp, fp, C.c_int, rp, vp, vp]),
             "gpo_obs2d_train": (vp, [fp, fp, C.c_int, C.c_int]),
@@ -75,8 +75,8 @@ class Oracle:
     def gp_train(self, dim, samples, scale, noise):
         return OracleGP(self, dim, samples, scale, noise)
 
-    def make_map(self, dim, centres, cluster_half, gps, search_half, var_thre, noise):
-        return OracleMap(self, dim, centres, cluster_half, gps, search_half, var_thre, noise)
+    def make_map(self, dim, centres, cluster_half, gps, search_half, var_thre, noise, boxes=None):
+        return OracleMap(self, dim, centres, cluster_half, gps, search_half, var_thre, noise, boxes)
 
     def obs2d(self, vu, zinv, ni, nj):
         return OracleObs(self, 2, np.ascontiguousarray(vu, np.float32).ravel(),
@@ -124,13 +124,15 @@ class OracleGP:
 
 
 class OracleMap:
-    def __init__(self, o, dim, centres, cluster_half, gps, search_half, var_thre, noise):
+    def __init__(self, o, dim, centres, cluster_half, gps, search_half, var_thre, noise, boxes=None):
         self.o = o
         self.dim = dim
         self.gps = list(gps)  # keep alive
         c = np.ascontiguousarray(centres, np.float32)
         arr = (C.c_void_p * max(len(gps), 1))(*[(g.h if g is not None else None) for g in gps])
-        self.h = o.L.gpo_map_create(dim, len(gps), c, cluster_half, arr, search_half, var_thre, noise)
+        b = np.ascontiguousarray(boxes, np.float32) if boxes is not None else None
+        bp = b.ctypes.data_as(C.c_void_p) if b is not None else None
+        self.h = o.L.gpo_map_create(dim, len(gps), c, cluster_half, arr, search_half, var_thre, noise, bp)
 
     def test(self, x, res=None, want_choice=False):
         x = np.ascontiguousarray(x, np.float32)

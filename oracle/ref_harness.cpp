@@ -289,6 +289,40 @@ int ref3_clusters(void* m_, float* centres, int* nsamples, int* trained, int cap
     }
     return (int)oc.size();
 }
+// Effective box of every non-empty cluster (DFS order): intersection of the float AABBs of the
+// cluster and all its ancestors — what the level-by-level pruning of QueryNonEmptyLevelC
+// (octree.cpp:864-867) amounts to. boxes: n x 6 floats (lo xyz, hi xyz).
+int ref3_cluster_boxes(void* m_, float* boxes, int cap) {
+    GPisMap3* m = (GPisMap3*)m_;
+    if (m->t == 0) return 0;
+    std::vector<OcTree*> oc;
+    m->t->QueryNonEmptyLevelC(AABB3(0.f, 0.f, 0.f, HUGE_HALF), oc);
+    for (int i = 0; i < (int)oc.size() && i < cap; ++i) {
+        float lo[3] = {-3e38f, -3e38f, -3e38f}, hi[3] = {3e38f, 3e38f, 3e38f};
+        for (OcTree* q = oc[i]; q != 0; q = q->getParent()) {
+            lo[0] = std::max(lo[0], q->boundary.getXMinbound()); hi[0] = std::min(hi[0], q->getXMaxbound());
+            lo[1] = std::max(lo[1], q->getYMinbound()); hi[1] = std::min(hi[1], q->getYMaxbound());
+            lo[2] = std::max(lo[2], q->getZMinbound()); hi[2] = std::min(hi[2], q->getZMaxbound());
+        }
+        for (int c = 0; c < 3; ++c) { boxes[6 * i + c] = lo[c]; boxes[6 * i + 3 + c] = hi[c]; }
+    }
+    return (int)oc.size();
+}
+int ref2_cluster_boxes(void* m_, float* boxes, int cap) {
+    GPisMap* m = (GPisMap*)m_;
+    if (m->t == 0) return 0;
+    std::vector<QuadTree*> oc;
+    m->t->QueryNonEmptyLevelC(AABB(0.f, 0.f, HUGE_HALF), oc);
+    for (int i = 0; i < (int)oc.size() && i < cap; ++i) {
+        float lo[2] = {-3e38f, -3e38f}, hi[2] = {3e38f, 3e38f};
+        for (QuadTree* q = oc[i]; q != 0; q = q->getParent()) {
+            lo[0] = std::max(lo[0], q->boundary.getXMinbound()); hi[0] = std::min(hi[0], q->boundary.getXMaxbound());
+            lo[1] = std::max(lo[1], q->boundary.getYMinbound()); hi[1] = std::min(hi[1], q->boundary.getYMaxbound());
+        }
+        for (int c = 0; c < 2; ++c) { boxes[4 * i + c] = lo[c]; boxes[4 * i + 2 + c] = hi[c]; }
+    }
+    return (int)oc.size();
+}
 void ref3_root(void* m_, float* c_half) {
     GPisMap3* m = (GPisMap3*)m_;
     c_half[0] = c_half[1] = c_half[2] = c_half[3] = 0.f;

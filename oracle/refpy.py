@@ -63,6 +63,8 @@ def lib():
             "ref3_all_samples": (C.c_int, [vp, vp, C.c_int]),
             "ref3_clusters": (C.c_int, [vp, vp, vp, vp, C.c_int]),
             "ref3_root": (None, [vp, f32p]),
+            "ref3_cluster_boxes": (C.c_int, [vp, vp, C.c_int]),
+            "ref2_cluster_boxes": (C.c_int, [vp, vp, C.c_int]),
             "ref3_train_set": (C.c_int, [vp, f32p, C.c_float, C.c_float, vp, C.c_int]),
             "ref3_cluster_gp": (C.c_int, [vp, f32p, vp, vp, vp, C.c_int]),
             "ref3_candidates": (C.c_int, [vp, f32p, C.c_float, f32p, f32p, C.c_int]),
@@ -174,6 +176,14 @@ class _RefMapBase:
         if n:
             self._fn("clusters")(self.h, _ptr(c), _ptr(ns), _ptr(tr), n)
         return c, ns, tr
+
+    def cluster_boxes(self):
+        """Effective (ancestor-intersected) float boxes of the non-empty clusters, DFS order: (n, 2*dim)."""
+        n = self._fn("clusters")(self.h, None, None, None, 0)
+        b = np.zeros((n, 2 * self.dim), np.float32)
+        if n:
+            self._fn("cluster_boxes")(self.h, _ptr(b), n)
+        return b
 
     def root(self):
         r = np.zeros(4, np.float32)

@@ -1,0 +1,112 @@
+"""Shared input generators and comparison helpers for the parity tests (seeded, size-bounded)."""
+import numpy as np
+
+# reference defaults (cpp/include/params.h)
+P3 = dict(dim=3, scale=0.04, noise=5e-3, half=0.025, rtimes=2.0, search=0.025 * 3.0, var_thre=0.5)
+P2 = dict(dim=2, scale=1.2, noise=1e-2, half=0.8, rtimes=4.0, search=1.2 * 4.0, var_thre=0.4)
+
+
+def leaf_samples3(N, rng, spread=0.05, flat=True):
+    """N samples of a gently curved surface patch inside a training ball, 9 floats each."""
+    p = rng.uniform(-spread, spread, (N, 3))
+    p[:, 2] = 0.01 * np.sin(40 * p[:, 0]) + 0.2 * p[:, 1] if flat else p[:, 2]
+    g = np.stack([-0.4 * np.cos(40 * p[:, 0]), -0.2 * np.ones(N), np.ones(N)], 1)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    s = np.zeros((N, 9), np.float32)
+    s[:, :3] = p + np.array([0.3125, -0.1375, 0.0625])
+    s[:, 3:6] = g
+    s[:, 6] = -0.2
+    s[:, 7] = rng.uniform(1e-3, 8e-3, N)
+    s[:, 8] = rng.uniform(0.01, 0.12, N)   # some above the 0.1001 gradflag threshold
+    if N > 3:
+        s[::7, 3:6] = 0                     # some with a null normal
+    return s
+
+
+def leaf_samples2(N, rng):
+    s = np.zeros((N, 7), np.float32)
+    s[:, 0] = np.sort(rng.uniform(-3, 3, N))
+    s[:, 1] = 0.3 * np.sin(s[:, 0]) + rng.normal(0, 0.01, N)
+    g = np.stack([-0.3 * np.cos(s[:, 0]), np.ones(N)], 1)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    s[:, 2:4] = g
+    s[:, 4] = -0.2
+    s[:, 5] = rng.uniform(0.01, 0.05, N)
+    s[:, 6] = rng.uniform(0.01, 0.12, N)
+    if N > 3:
+        s[::9, 2:4] = 0
+    return s
+
+
+def sphere_samples(radius, spacing, centre, rng, noise=True):
+    """Roughly even samples on a sphere (Fibonacci lattice) with outward normals."""
+    n = int(4 * np.pi * radius ** 2 / spacing ** 2)
+    k = np.arange(n) + 0.5
+    phi = np.arccos(1 - 2 * k / n)
+    th = np.pi * (1 + 5 ** 0.5) * k
+    d = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
+    s = np.zeros((n, 9), np.float32)
+    s[:, :3] = d * radius + np.asarray(centre)
+    s[:, 3:6] = d
+    s[:, 6] = -0.2
+    s[:, 7] = rng.uniform(1e-3, 6e-3, n) if noise else 2e-3
+    s[:, 8] = rng.uniform(0.01, 0.09, n) if noise else 0.02
+    return s
+
+
+def circle_samples(radius, spacing, centre, rng):
+    n = int(2 * np.pi * radius / spacing)
+    th = 2 * np.pi * (np.arange(n) + 0.37) / n
+    d = np.stack([np.cos(th), np.sin(th)], 1)
+    s = np.zeros((n, 7), np.float32)
+    s[:, :2] = d * radius + np.asarray(centre)
+    s[:, 2:4] = d
+    s[:, 4] = -0.2
+    s[:, 5] = rng.uniform(0.01, 0.03, n)
+    s[:, 6] = rng.uniform(0.01, 0.09, n)
+    return s
+
+
+def ref_map_to_csr(refmap, P):
+    """Clusters (DFS order), their training sets in QueryRange order, as the CSR the C ABI takes."""
+    centres, nsamp, trained = refmap.clusters()
+    offs = [0]
+    chunks = []
+    for c in centres:
+        ts = refmap.train_set(c, P["half"], P["rtimes"])
+        chunks.append(ts)
+        offs.append(offs[-1] + ts.shape[0])
+    w = 2 * P["dim"] + 3
+    samples = np.concatenate(chunks, 0) if chunks else np.zeros((0, w), np.float32)
+    return centres, np.asarray(offs, np.int32), samples, trained
+
+
+def root_cells(refmap, P):
+    c, half = refmap.root()
+    pitch = 2.0 * np.float64(np.float32(P["half"]))
+    root_min = np.round((c.astype(np.float64) - half) / pitch).astype(np.int32)
+    levels = int(round(np.log2(half / np.float64(np.float32(P["half"])))))
+    return root_min, levels
+
+
+def rel_err(a, b, floor=0.0):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def check_rows(got, want, dim, tol_f=1e-4, tol_v=1e-3, label=""):
+    """north_star tolerances: rel 1e-4 on f and grad (grad: vector-norm relative with an absolute
+    floor), rel 1e-3 on variances."""
+    w = 1 + dim
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    ef = np.abs(got[:, 0] - want[:, 0]) / np.maximum(np.abs(want[:, 0]), 1e-3)
+    gn = np.linalg.norm(want[:, 1:w], axis=1)
+    eg = np.linalg.norm(got[:, 1:w] - want[:, 1:w], axis=1) / np.maximum(gn, 1e-2)
+    ev = np.abs(got[:, w:] - want[:, w:]) / np.maximum(np.abs(want[:, w:]), 1e-3)
+    msg = f"{label} f {ef.max():.2e} grad {eg.max():.2e} var {ev.max():.2e}"
+    assert ef.max() < tol_f, msg
+    assert eg.max() < tol_f, msg
+    assert ev.max() < tol_v, msg
+    return ef.max(), eg.max(), ev.max()

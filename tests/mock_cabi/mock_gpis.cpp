@@ -1,0 +1,200 @@
+// TEST SCAFFOLDING ONLY. A CPU stand-in for libgpis_b200.so that implements the same C ABI
+// (include/gpis_b200.h) on top of the plain-C oracle (oracle/gpis_oracle.c). It exists so the
+// host-side logic of the drop-in classes (tree, evalPoints / reEvalPoints heuristics, dirty-leaf
+// CSR, table sync) can be validated against oracle/_ref in a container without a GPU. It is built
+// into tests/_mock/ by tests/mockbuild.py, never into gpismap_b200/, and nothing in the product
+// path can load it.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gpis_b200.h"
+#include "gpis_oracle.h"
+
+struct MockLeaf {
+    int32_t cell[3];
+    float centre[3];
+    float lo[3], hi[3];
+    bool box_set = false;
+    gpo_gp* gp = nullptr;
+    int N = 0;
+    int index = 0;
+};
+struct gpis_ctx {
+    gpis_config cfg;
+    std::string err;
+    std::map<std::vector<int32_t>, MockLeaf> leaves;
+    int next_index = 0;
+    int32_t root_min[3] = {-(1 << 19), -(1 << 19), -(1 << 19)};
+    int levels = 20;
+    gpo_obs* obs = nullptr;
+    int obs_d = 0;
+    gpis_stats st{};
+};
+
+static uint64_t spread3(uint64_t v) {
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x1F00000000FFFFull;
+    v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+static uint64_t dfs_key(const gpis_ctx* c, const int32_t* cell) {
+    const uint32_t mask = (1u << c->levels) - 1u;
+    const uint32_t lx = (uint32_t)(cell[0] - c->root_min[0]) & mask;
+    const uint32_t ly = (~(uint32_t)(cell[1] - c->root_min[1])) & mask;
+    const uint32_t lz = c->cfg.dim == 3 ? ((~(uint32_t)(cell[2] - c->root_min[2])) & mask) : 0u;
+    return spread3(lx) | (spread3(ly) << 1) | (spread3(lz) << 2);
+}
+
+extern "C" {
+
+int gpis_config_default(gpis_config* cfg, int dim) {
+    if (!cfg || (dim != 2 && dim != 3)) return GPIS_ERR_ARG;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->dim = dim;
+    if (dim == 3) { cfg->map_scale = 0.04f; cfg->map_noise = 5e-3f; cfg->cluster_half = (float)0.025; cfg->search_half = (float)0.025 * 3.0; cfg->var_thre = 0.5f; }
+    else { cfg->map_scale = 1.2f; cfg->map_noise = 1e-2f; cfg->cluster_half = (float)0.8; cfg->search_half = 1.2f * 4.0; cfg->var_thre = 0.4f; }
+    cfg->obs_scale = 0.5f; cfg->obs_noise = 0.01f; cfg->max_leaves = 1 << 16; cfg->arena_chunk_bytes = 1ull << 30;
+    return GPIS_OK;
+}
+int gpis_create(gpis_ctx** out, const gpis_config* cfg) { *out = new gpis_ctx(); (*out)->cfg = *cfg; return GPIS_OK; }
+static void drop_all(gpis_ctx* c) {
+    for (auto& kv : c->leaves) gpo_gp_free(kv.second.gp);
+    c->leaves.clear();
+    if (c->obs) gpo_obs_free(c->obs);
+    c->obs = nullptr;
+}
+void gpis_destroy(gpis_ctx* c) { if (c) { drop_all(c); delete c; } }
+int gpis_reset(gpis_ctx* c) { drop_all(c); c->next_index = 0; return GPIS_OK; }
+const char* gpis_last_error(const gpis_ctx* c) { return c ? c->err.c_str() : ""; }
+int gpis_device(const gpis_ctx*) { return -1; }
+
+int gpis_leaves_update(gpis_ctx* c, int n, const int32_t* cells, const float* centres, const int32_t* offsets,
+                       const float* samples, int32_t* status) {
+    const int dim = c->cfg.dim, w = 2 * dim + 3;
+    c->st.last_train_leaves = 0;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int32_t> key(cells + (size_t)i * dim, cells + (size_t)(i + 1) * dim);
+        MockLeaf& L = c->leaves[key];
+        if (L.N == 0 && L.gp == nullptr && L.index == 0 && c->leaves.size() > (size_t)c->next_index) L.index = c->next_index++;
+        for (int a = 0; a < dim; ++a) { L.cell[a] = key[a]; L.centre[a] = centres[(size_t)i * dim + a]; }
+        const int N = offsets[i + 1] - offsets[i];
+        if (status) status[i] = 0;
+        if (N <= 0) continue;
+        gpo_gp_free(L.gp);
+        L.gp = gpo_gp_train(dim, samples + (size_t)offsets[i] * w, N, c->cfg.map_scale, c->cfg.map_noise);
+        L.N = N;
+        if (status) status[i] = gpo_gp_chol_fail(L.gp);
+        c->st.last_train_leaves++;
+    }
+    return GPIS_OK;
+}
+int gpis_leaves_mark(gpis_ctx* c, int n, const int32_t* cells, const float* centres) {
+    const int dim = c->cfg.dim;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int32_t> key(cells + (size_t)i * dim, cells + (size_t)(i + 1) * dim);
+        if (c->leaves.count(key)) continue;
+        MockLeaf& L = c->leaves[key];
+        L.index = c->next_index++;
+        for (int a = 0; a < dim; ++a) { L.cell[a] = key[a]; L.centre[a] = centres[(size_t)i * dim + a]; }
+    }
+    return GPIS_OK;
+}
+int gpis_leaves_set_boxes(gpis_ctx* c, int n, const int32_t* cells, const float* boxes) {
+    const int dim = c->cfg.dim;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int32_t> key(cells + (size_t)i * dim, cells + (size_t)(i + 1) * dim);
+        auto it = c->leaves.find(key);
+        if (it == c->leaves.end()) continue;
+        for (int a = 0; a < dim; ++a) { it->second.lo[a] = boxes[(size_t)i * 2 * dim + a]; it->second.hi[a] = boxes[(size_t)i * 2 * dim + dim + a]; }
+        it->second.box_set = true;
+    }
+    return GPIS_OK;
+}
+int gpis_leaves_erase(gpis_ctx* c, int n, const int32_t* cells) {
+    const int dim = c->cfg.dim;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int32_t> key(cells + (size_t)i * dim, cells + (size_t)(i + 1) * dim);
+        auto it = c->leaves.find(key);
+        if (it == c->leaves.end()) continue;
+        gpo_gp_free(it->second.gp);
+        c->leaves.erase(it);
+    }
+    return GPIS_OK;
+}
+int gpis_rebase(gpis_ctx* c, const int32_t* rm, int levels) {
+    for (int a = 0; a < 3; ++a) c->root_min[a] = a < c->cfg.dim ? rm[a] : 0;
+    c->levels = levels;
+    return GPIS_OK;
+}
+int gpis_leaf_index(gpis_ctx* c, const int32_t* cell) {
+    std::vector<int32_t> key(cell, cell + c->cfg.dim);
+    auto it = c->leaves.find(key);
+    return it == c->leaves.end() ? -1 : it->second.index;
+}
+int gpis_leaf_get(gpis_ctx* c, const int32_t* cell, int32_t* N, int32_t* ng, float* alpha, float* L, float* gradflag, int cap_n) {
+    std::vector<int32_t> key(cell, cell + c->cfg.dim);
+    auto it = c->leaves.find(key);
+    if (it == c->leaves.end() || !it->second.gp) return 0;
+    const int n = gpo_gp_n(it->second.gp);
+    if (N) *N = it->second.N;
+    if (ng) *ng = gpo_gp_ng(it->second.gp);
+    if (n <= cap_n) gpo_gp_get(it->second.gp, alpha, L, gradflag);
+    return n;
+}
+int gpis_query(gpis_ctx* c, const float* x, int64_t n, float* res) {
+    const int dim = c->cfg.dim;
+    std::vector<std::pair<uint64_t, const MockLeaf*>> order;
+    for (auto& kv : c->leaves) order.push_back({dfs_key(c, kv.second.cell), &kv.second});
+    std::sort(order.begin(), order.end(), [](const std::pair<uint64_t, const MockLeaf*>& a, const std::pair<uint64_t, const MockLeaf*>& b) { return a.first < b.first; });
+    std::vector<float> centres, boxes;
+    std::vector<gpo_gp*> gps;
+    for (auto& o : order) {
+        for (int a = 0; a < dim; ++a) centres.push_back(o.second->centre[a]);
+        for (int a = 0; a < dim; ++a) boxes.push_back(o.second->box_set ? o.second->lo[a] : o.second->centre[a] - c->cfg.cluster_half);
+        for (int a = 0; a < dim; ++a) boxes.push_back(o.second->box_set ? o.second->hi[a] : o.second->centre[a] + c->cfg.cluster_half);
+        gps.push_back(o.second->gp);
+    }
+    gpo_map* m = gpo_map_create(dim, (int)gps.size(), centres.data(), c->cfg.cluster_half, gps.data(), c->cfg.search_half, c->cfg.var_thre, c->cfg.map_noise, boxes.data());
+    gpo_map_test(m, x, (int)n, res, nullptr, nullptr);
+    gpo_map_free(m);
+    return GPIS_OK;
+}
+int gpis_query_device(gpis_ctx*, const float*, int64_t, float*) { return GPIS_ERR_STATE; }
+int gpis_query_debug(gpis_ctx* c, const float* x, int64_t n, float* res, int32_t*, int32_t*) { return gpis_query(c, x, n, res); }
+
+int gpis_obs_train_2d(gpis_ctx* c, const float* vu, const float* zinv, int ni, int nj) {
+    gpo_obs* prev = (c->obs && c->obs_d == 2) ? c->obs : nullptr;
+    gpo_obs* now = gpo_obs2d_retrain(vu, zinv, ni, nj, prev);
+    if (c->obs) gpo_obs_free(c->obs);
+    c->obs = now;
+    c->obs_d = 2;
+    return GPIS_OK;
+}
+int gpis_obs_train_1d(gpis_ctx* c, const float* th, const float* f, int n) {
+    if (c->obs) gpo_obs_free(c->obs);
+    c->obs = gpo_obs1d_train(th, f, n);
+    c->obs_d = 1;
+    return GPIS_OK;
+}
+int gpis_obs_test(gpis_ctx* c, const float* xt, int d, int m, float* val, float* var) {
+    if (!c->obs || d != c->obs_d) return GPIS_OK;
+    gpo_obs_test(c->obs, xt, m, val, var);
+    return GPIS_OK;
+}
+int gpis_export_dirty(gpis_ctx*, const void**, uint64_t*) { return GPIS_ERR_STATE; }
+int gpis_import(gpis_ctx*, const void*, uint64_t) { return GPIS_ERR_STATE; }
+int gpis_get_stats(gpis_ctx* c, gpis_stats* out) {
+    c->st.leaves = (int64_t)c->leaves.size();
+    *out = c->st;
+    return GPIS_OK;
+}
+int gpis_set_eval_version(gpis_ctx*, int) { return GPIS_OK; }
+
+}  // extern "C"
