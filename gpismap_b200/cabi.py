@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libgpis_b200.so")
 
 EXPORTS = [
     "gpis_config_default", "gpis_create", "gpis_destroy", "gpis_reset", "gpis_last_error", "gpis_device",
-    "gpis_leaves_update", "gpis_leaves_mark", "gpis_leaves_set_boxes", "gpis_leaves_erase", "gpis_rebase", "gpis_leaf_get",
+    "gpis_leaves_update", "gpis_leaves_mark", "gpis_leaves_set_boxes", "gpis_leaves_erase", "gpis_rebase", "gpis_get_rebase", "gpis_leaf_get",
     "gpis_query", "gpis_query_device", "gpis_query_debug", "gpis_leaf_index",
     "gpis_obs_train_2d", "gpis_obs_train_1d", "gpis_obs_test",
     "gpis_export_dirty", "gpis_import", "gpis_get_stats",
@@ -67,6 +67,7 @@ def lib():
         L.gpis_leaves_erase.argtypes = [vp, C.c_int, vp]
         L.gpis_leaves_set_boxes.argtypes = [vp, C.c_int, vp, vp]
         L.gpis_rebase.argtypes = [vp, vp, C.c_int]
+        L.gpis_get_rebase.argtypes = [vp, vp, C.POINTER(C.c_int)]
         L.gpis_leaf_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.gpis_query.argtypes = [vp, vp, i64, vp]
         L.gpis_query_device.argtypes = [vp, vp, i64, vp]
@@ -104,9 +105,13 @@ def cells_of(centres, cluster_half):
 class Ctx:
     """Thin owner of a gpis_ctx."""
 
-    def __init__(self, dim=3, device=0, cfg=None):
+    def __init__(self, dim=3, device=0, cfg=None, borrowed=None):
         self.cfg = cfg if cfg is not None else default_config(dim, device)
         self.dim = self.cfg.dim
+        self.borrowed = borrowed is not None
+        if self.borrowed:      # a gpis_ctx* owned by someone else (e.g. a GPisMap3): never destroyed here
+            self.h = C.c_void_p(borrowed)
+            return
         self.h = C.c_void_p()
         rc = lib().gpis_create(C.byref(self.h), C.byref(self.cfg))
         if rc != 0:
@@ -119,7 +124,8 @@ class Ctx:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().gpis_destroy(self.h)
+            if not self.borrowed:
+                lib().gpis_destroy(self.h)
             self.h = None
 
     __del__ = close
@@ -130,6 +136,12 @@ class Ctx:
     def rebase(self, root_min_cell, levels):
         r = np.ascontiguousarray(root_min_cell, np.int32)
         self._ck(lib().gpis_rebase(self.h, _p(r), levels))
+
+    def get_rebase(self):
+        r = np.zeros(3, np.int32)
+        lv = C.c_int(0)
+        self._ck(lib().gpis_get_rebase(self.h, _p(r), C.byref(lv)))
+        return r, lv.value
 
     def leaves_update(self, cells, centres, offsets, samples):
         cells = np.ascontiguousarray(cells, np.int32)

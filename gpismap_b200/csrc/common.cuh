@@ -25,7 +25,8 @@ struct LeafHeader {
     uint64_t key;
     int32_t cell[4];
     float centre[4];
-    uint8_t pad[128 - 32 - 16 - 16 - 16];
+    float lo[4], hi[4];   // effective candidate box (see gpis_leaves_set_boxes)
+    uint8_t pad[128 - 32 - 16 - 16 - 16 - 32];
 };
 static_assert(sizeof(LeafHeader) == 128, "header must be 128 bytes");
 

@@ -145,6 +145,7 @@ struct gpis_ctx {
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
+    double* d_acc = nullptr;
     // obs gp
     ObsTile* obs_tiles = nullptr; int obs_tile_cap = 0;
     ObsTileDesc* obs_desc = nullptr;
@@ -368,7 +369,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->W.cand); cudaFree(ctx->W.tie); cudaFree(ctx->W.evalout); cudaFree(ctx->W.pairs); cudaFree(ctx->W.counters);
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
-    cudaFree(ctx->d_export);
+    cudaFree(ctx->d_export); cudaFree(ctx->d_acc);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -405,6 +406,13 @@ int gpis_rebase(gpis_ctx* ctx, const int32_t* root_min_cell, int levels) {
     if (!ctx || !root_min_cell || levels < 0 || levels > 20) return GPIS_ERR_ARG;
     for (int c = 0; c < 3; ++c) ctx->qp.root_min[c] = (c < ctx->cfg.dim) ? root_min_cell[c] : 0;
     ctx->qp.levels = levels;
+    return GPIS_OK;
+}
+
+int gpis_get_rebase(gpis_ctx* ctx, int32_t* root_min_cell, int* levels) {
+    if (!ctx || !root_min_cell || !levels) return GPIS_ERR_ARG;
+    for (int c = 0; c < 3; ++c) root_min_cell[c] = ctx->qp.root_min[c];
+    *levels = ctx->qp.levels;
     return GPIS_OK;
 }
 
@@ -557,7 +565,7 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
         hl.rec = rec; hl.rec_bytes = rb; hl.N = N; hl.ng = ng; hl.n = n; hl.nb = nb;
         TrainJob j{};
         j.rec = rec; j.sample_off = offsets[i]; j.N = N; j.ng = ng; j.n = n; j.nb = nb; j.slot = hl.slot;
-        for (int c = 0; c < 3; ++c) { j.cell[c] = hl.cell[c]; j.centre[c] = hl.centre[c]; }
+        for (int c = 0; c < 3; ++c) { j.cell[c] = hl.cell[c]; j.centre[c] = hl.centre[c]; j.lo[c] = hl.lo[c]; j.hi[c] = hl.hi[c]; }
         jobs.push_back(j);
         job_leaf.push_back(i);
         ups.push_back(make_update(key, hl));
@@ -667,11 +675,11 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
         ctx->work_cap = cap;
     }
     QueryWork W = ctx->W;
-    if (!h_tie) W.tie = nullptr;
     double flops = 0, bytes_g = 0;
     int64_t evals = 0;
     float ms_total = 0.f, ms_eval = 0.f;
-    std::vector<int2> hpairs;
+    if (!ctx->d_acc) CK(cudaMalloc(&ctx->d_acc, sizeof(double) * 4));
+    CK(cudaMemsetAsync(ctx->d_acc, 0, sizeof(double) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (int64_t q0 = 0; q0 < n; q0 += CH) {
         const int64_t nq = std::min<int64_t>(CH, n - q0);
@@ -680,7 +688,8 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
         const int gq = (int)((nq + 255) / 256);
         CK(cudaMemsetAsync(W.counters, 0, sizeof(int32_t) * 16, ctx->stream));
         k_candidates<<<gq, 256, 0, ctx->stream>>>(xq, nq, rq, ctx->T, ctx->qp, W);
-        ctx->st.kernel_launches++;
+        k_candidates_exact<<<(int)((nq + 127) / 128), 128, 0, ctx->stream>>>(xq, nq, ctx->T, ctx->qp, W);
+        ctx->st.kernel_launches += 2;
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 1) {
                 CK(cudaMemsetAsync(W.counters, 0, sizeof(int32_t) * 16, ctx->stream));
@@ -692,15 +701,13 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
             CK(cudaStreamSynchronize(ctx->stream));
             if (npairs > 0) {
                 CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-                if (ctx->eval_version == 1) {
-                    const int smem = (1 + dim) * ctx->max_nb * 32 * (int)sizeof(float);
-                    for (int p0 = 0; p0 < npairs; p0 += 1 << 30) {
-                        k_eval_v1<<<npairs, EVAL1_THREADS, smem, ctx->stream>>>(xq, ctx->T, ctx->qp, W, 0);
-                        ctx->st.kernel_launches++;
-                    }
-                } else {
+                {
+                    // v2 keeps the right-hand sides of 8 queries in shared memory: nb <= 40 (n <= 1280)
+                    const bool use_v1 = ctx->eval_version == 1 || Eval2Smem::total(ctx->max_nb) > 227 * 1024;
+                    const int smem1 = (1 + dim) * ctx->max_nb * 32 * (int)sizeof(float);
                     int rc = query_v2_eval(ctx->stream, xq, ctx->T, ctx->qp, W, npairs, ctx->slot_count, ctx->max_nb,
-                                           &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err);
+                                           &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err, ctx->d_acc,
+                                           use_v1, smem1);
                     if (rc) return rc;
                 }
                 CK(cudaGetLastError());
@@ -726,6 +733,13 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
     ctx->st.last_query_evals = evals;
     ctx->st.last_query_ms = ms_total;
     ctx->st.last_query_eval_ms = ms_eval;
+    double acc[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(acc, ctx->d_acc, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+    ctx->st.last_query_flops = acc[0];
+    ctx->st.last_query_bytes_gather = 44.0 * (double)n + acc[1];
+    // compulsory bytes: every leaf record touched counts once per pass over the batch (two passes and
+    // query chunks may touch a leaf again; that is real re-reading and is charged)
+    ctx->st.last_query_bytes_compulsory = 44.0 * (double)n + acc[2];
     (void)flops; (void)bytes_g;
     return GPIS_OK;
 }
@@ -964,6 +978,8 @@ int gpis_import(gpis_ctx* ctx, const void* buf_device, uint64_t bytes) {
         if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
         hl.rec = rec; hl.rec_bytes = h.bytes; hl.N = h.N; hl.ng = h.ng; hl.n = h.n; hl.nb = h.nb;
         set_geometry(ctx, hl, h.cell, h.centre);
+        for (int c = 0; c < 3; ++c) { hl.lo[c] = h.lo[c]; hl.hi[c] = h.hi[c]; }
+        hl.box_set = true;
         ctx->max_nb = std::max(ctx->max_nb, h.nb);
         ctx->max_N = std::max(ctx->max_N, h.N);
         ups.push_back(make_update(h.key, hl));

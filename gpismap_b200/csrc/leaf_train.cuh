@@ -31,6 +31,7 @@ struct TrainJob {
     int32_t slot;
     int32_t cell[3];
     float centre[3];
+    float lo[3], hi[3];
 };
 
 struct TrainParams {
@@ -460,8 +461,8 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         h->N = N; h->ng = ng; h->n = n; h->nb = nb; h->dim = dim; h->chol_fail = bad_total; h->slot = job.slot;
         h->bytes = rec_bytes(N, nb);
         h->key = cell_key(job.cell[0], job.cell[1], dim == 3 ? job.cell[2] : 0);
-        for (int c = 0; c < 3; ++c) { h->cell[c] = job.cell[c]; h->centre[c] = job.centre[c]; }
-        h->cell[3] = 0; h->centre[3] = 0.f;
+        for (int c = 0; c < 3; ++c) { h->cell[c] = job.cell[c]; h->centre[c] = job.centre[c]; h->lo[c] = job.lo[c]; h->hi[c] = job.hi[c]; }
+        h->cell[3] = 0; h->centre[3] = 0.f; h->lo[3] = 0.f; h->hi[3] = 0.f;
         if (status) status[blockIdx.x] = bad_total;
     }
 }

@@ -96,15 +96,136 @@ k_candidates(const float* __restrict__ x, int64_t nq, float* __restrict__ res, L
             }
     const int numc = min(nc, 3);
     W.cand[q] = make_int4(nc, numc > 0 ? bi[0] : -1, numc > 1 ? bi[1] : -1, numc > 2 ? bi[2] : -1);
-    if (W.tie) {
-        int t = 0;
-        for (int k = 0; k < numc && k + 1 < nc; ++k)
-            if (bs[k] == bs[k + 1]) t = 1;
-        W.tie[q] = t;
-    }
+    int t = 0;
+    for (int k = 0; k < numc && k + 1 < nc; ++k)
+        if (bs[k] == bs[k + 1]) t = 1;
+    W.tie[q] = t;
+    // More than 16 candidates with an exact distance tie among the picks: the reference's std::sort
+    // (introsort) does not keep DFS order there; k_candidates_exact replays it.
+    if (t && nc > 16) return;
     if (nc > 0 && T.rec[bi[0]] != 0ull) {
         const int p = atomicAdd(&W.counters[0], 1);
         W.pairs[p] = make_int2((int)q, bi[0]);
+    }
+}
+
+// ------------------------------------------------------------------ exact std::sort replay
+// libstdc++ (GCC 13, bits/stl_algo.h) std::sort on the candidate index array with comparator
+// sqdst[i1] < sqdst[i2], started from the tree's DFS order — what GPisMap3.cpp:826-829 executes.
+// Only queries with > 16 candidates AND an exact tie among the picks come here (a symmetric query
+// grid, e.g. the reference's own demo grids, produces them).
+#define GPIS_MAXC 256
+struct CandList { float key[GPIS_MAXC]; int slot[GPIS_MAXC]; };
+
+__device__ inline void ssr_swap(CandList& L, int a, int b) {
+    const float tk = L.key[a]; L.key[a] = L.key[b]; L.key[b] = tk;
+    const int ts = L.slot[a]; L.slot[a] = L.slot[b]; L.slot[b] = ts;
+}
+__device__ inline void ssr_unguarded_linear_insert(CandList& L, int last) {
+    const float vk = L.key[last]; const int vs = L.slot[last];
+    int next = last - 1;
+    while (vk < L.key[next]) { L.key[last] = L.key[next]; L.slot[last] = L.slot[next]; last = next; --next; }
+    L.key[last] = vk; L.slot[last] = vs;
+}
+__device__ inline void ssr_insertion_sort(CandList& L, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (L.key[i] < L.key[first]) {
+            const float vk = L.key[i]; const int vs = L.slot[i];
+            for (int j = i; j > first; --j) { L.key[j] = L.key[j - 1]; L.slot[j] = L.slot[j - 1]; }
+            L.key[first] = vk; L.slot[first] = vs;
+        } else ssr_unguarded_linear_insert(L, i);
+    }
+}
+__device__ inline void std_sort_replay(CandList& L, int n) {
+    if (n <= 1) return;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    // __introsort_loop, recursion on the right part turned into an explicit stack
+    int stk_first[32], stk_last[32], stk_depth[32], sp = 0;
+    stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        // the reference recurses into [cut, last) FIRST and then continues with [first, cut):
+        // the two sub-ranges are disjoint, so the order of processing does not change the result.
+        while (last - first > 16) {
+            if (depth == 0) { ssr_insertion_sort(L, first, last); break; }
+            --depth;
+            const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+            int med;
+            if (L.key[a] < L.key[b]) { if (L.key[b] < L.key[c]) med = b; else if (L.key[a] < L.key[c]) med = c; else med = a; }
+            else if (L.key[a] < L.key[c]) med = a;
+            else if (L.key[b] < L.key[c]) med = c;
+            else med = b;
+            ssr_swap(L, first, med);
+            int lo = first + 1, hi = last;
+            for (;;) {
+                while (L.key[lo] < L.key[first]) ++lo;
+                --hi;
+                while (L.key[first] < L.key[hi]) --hi;
+                if (!(lo < hi)) break;
+                ssr_swap(L, lo, hi);
+                ++lo;
+            }
+            if (sp < 32) { stk_first[sp] = lo; stk_last[sp] = last; stk_depth[sp] = depth; ++sp; }
+            last = lo;
+        }
+    }
+    if (n > 16) {
+        ssr_insertion_sort(L, 0, 16);
+        for (int i = 16; i != n; ++i) ssr_unguarded_linear_insert(L, i);
+    } else ssr_insertion_sort(L, 0, n);
+}
+
+__global__ void __launch_bounds__(128)
+k_candidates_exact(const float* __restrict__ x, int64_t nq, LeafTable T, QueryParams P, QueryWork W) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    if (W.tie[q] == 0 || W.cand[q].x <= 16) return;
+    const int dim = P.dim;
+    float xq[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < dim; ++c) xq[c] = x[q * dim + c];
+    float qlo[3], qhi[3];
+    int clo[3] = {0, 0, 0}, chi[3] = {0, 0, 0};
+    for (int c = 0; c < dim; ++c) {
+        qlo[c] = xq[c] - P.search_half;
+        qhi[c] = xq[c] + P.search_half;
+        clo[c] = (int)floor((double)qlo[c] * P.inv_pitch - 1.0 - 1e-3);
+        chi[c] = (int)floor((double)qhi[c] * P.inv_pitch + 1e-3);
+    }
+    CandList L;
+    uint64_t dk[GPIS_MAXC];
+    int nc = 0;
+    for (int iz = clo[2]; iz <= chi[2]; ++iz)
+        for (int iy = clo[1]; iy <= chi[1]; ++iy)
+            for (int ix = clo[0]; ix <= chi[0]; ++ix) {
+                const int slot = table_find(T, cell_key(ix, iy, iz));
+                if (slot < 0) continue;
+                const float4 ct = T.centre[slot], bl = T.lo[slot], bh = T.hi[slot];
+                const float cc[3] = {ct.x, ct.y, ct.z};
+                const float blo[3] = {bl.x, bl.y, bl.z}, bhi[3] = {bh.x, bh.y, bh.z};
+                bool hit = true;
+                float sq = 0.f;
+                for (int c = 0; c < dim; ++c) {
+                    if (qhi[c] < blo[c] || qlo[c] > bhi[c]) hit = false;
+                    const float d = cc[c] - xq[c];
+                    sq = (c == 0) ? d * d : sq + d * d;
+                }
+                if (!hit || nc >= GPIS_MAXC) continue;
+                // keep the list in DFS order (insertion by DFS key)
+                const uint64_t k = dfs_key(P, T.cell[slot]);
+                int pos = nc;
+                while (pos > 0 && dk[pos - 1] > k) { dk[pos] = dk[pos - 1]; L.key[pos] = L.key[pos - 1]; L.slot[pos] = L.slot[pos - 1]; --pos; }
+                dk[pos] = k; L.key[pos] = sq; L.slot[pos] = slot;
+                ++nc;
+            }
+    std_sort_replay(L, nc);
+    const int numc = min(nc, 3);
+    W.cand[q] = make_int4(nc, numc > 0 ? L.slot[0] : -1, numc > 1 ? L.slot[1] : -1, numc > 2 ? L.slot[2] : -1);
+    if (nc > 0 && T.rec[L.slot[0]] != 0ull) {
+        const int p = atomicAdd(&W.counters[0], 1);
+        W.pairs[p] = make_int2((int)q, L.slot[0]);
     }
 }
 

@@ -83,6 +83,29 @@ __global__ void k_make_items(SortBufs S, int nslots) {
     for (int o = 0; o < c; o += QB) S.items[it++] = make_int4(s, S.start[s] + o, min(QB, c - o), 0);
 }
 
+// Algorithmic work of one evaluation pass, accumulated over leaves with work:
+//   acc[0] flops            sum over evaluations of 4n^2 + 16n + 80N
+//   acc[1] gather bytes     sum over evaluations of 16N + 4n + 2n(n+1)
+//   acc[2] compulsory bytes sum over DISTINCT leaves touched of the same record size
+__global__ void k_query_stats(SortBufs S, LeafTable T, int nslots, double* acc) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double f = 0, g = 0, c = 0;
+    if (s < nslots && S.count[s] > 0) {
+        const int4 m = T.meta[s];
+        const double N = m.x, n = m.z, cnt = S.count[s];
+        const double rec = 16.0 * N + 4.0 * n + 2.0 * n * (n + 1.0);
+        f = cnt * (4.0 * n * n + 16.0 * n + 80.0 * N);
+        g = cnt * rec;
+        c = rec;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        f += __shfl_xor_sync(0xffffffffu, f, o);
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (f != 0 || c != 0)) { atomicAdd(acc, f); atomicAdd(acc + 1, g); atomicAdd(acc + 2, c); }
+}
+
 struct Eval2Smem {
     static constexpr int off_bar = 0;                                         // EVAL2_WARPS * 2 mbarriers
     static constexpr int off_stage = 256;                                     // per warp 2 x 4 KB
@@ -286,7 +309,8 @@ static inline int query_v2_init(std::string& err) {
 // device buffer owned by the context.
 static inline int query_v2_eval(cudaStream_t st, const float* d_x, const LeafTable& T, const QueryParams& P,
                                 const QueryWork& W, int npairs, int nslots, int max_nb, int32_t** d_sort,
-                                int64_t* sort_cap, int64_t* launches, std::string& err) {
+                                int64_t* sort_cap, int64_t* launches, std::string& err, double* d_acc, bool use_v1,
+                                int v1_smem) {
 #define CK2(call)                                                                 \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -315,7 +339,14 @@ static inline int query_v2_eval(cudaStream_t st, const float* d_x, const LeafTab
     k_slot_scan<<<1, 1024, 0, st>>>(S, nslots);
     k_pair_scatter<<<(npairs + 255) / 256, 256, 0, st>>>(W.pairs, npairs, S);
     k_make_items<<<(nslots + 255) / 256, 256, 0, st>>>(S, nslots);
+    if (d_acc) { k_query_stats<<<(nslots + 255) / 256, 256, 0, st>>>(S, T, nslots, d_acc); *launches += 1; }
     *launches += 4;
+    if (use_v1) {   // reference-style one CTA per (query, leaf) pair; kept for leaves too large for v2's shared memory
+        k_eval_v1<<<npairs, EVAL1_THREADS, v1_smem, st>>>(d_x, T, P, W, 0);
+        *launches += 1;
+        CK2(cudaGetLastError());
+        return 0;
+    }
     int32_t nitems = 0;
     CK2(cudaMemcpyAsync(&nitems, S.totals, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK2(cudaStreamSynchronize(st));

@@ -82,10 +82,15 @@ public:
     // IsNotNew + Insert + registration, the block shared by evalPoints and reEvalPoints
     // (GPisMap3.cpp:608-623, 541-556). Returns the sample id when the point went in AND registered
     // at least one leaf; -1 otherwise (the sample may still sit in the tree).
-    int try_insert(const float* pos, std::vector<int>& touched) {
+    int try_insert(const float* pos, std::vector<int>& touched, const float* full = nullptr) {
         touched.clear();
         if (tree->is_not_new(pos)) return -1;
         const int s = tree->new_sample(pos);
+        if (full) {   // bulk load: the sample carries its data from the start, like ref_harness.cpp does
+            Sample<D>& sm = tree->sample(s);
+            for (int a = 0; a < D; ++a) sm.grad[a] = full[D + a];
+            sm.val = full[2 * D]; sm.pose_sig = full[2 * D + 1]; sm.grad_sig = full[2 * D + 2];
+        }
         const bool ok = tree->insert(s, touched);
         if (!ok || touched.empty()) return -1;
         return s;
@@ -264,11 +269,8 @@ public:
         int cnt = 0;
         for (int i = 0; i < n; ++i) {
             const float* s = smp + (size_t)i * W;
-            const int id = try_insert(s, touched);
+            const int id = try_insert(s, touched, s);
             if (id < 0) continue;
-            Sample<D>& sm = tree->sample(id);
-            for (int a = 0; a < D; ++a) sm.grad[a] = s[D + a];
-            sm.val = s[2 * D]; sm.pose_sig = s[2 * D + 1]; sm.grad_sig = s[2 * D + 2];
             activate(touched);
             ++cnt;
         }

@@ -112,6 +112,8 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells);
  * is the lattice cell of the root's minimum corner, levels = log2(root_half / cluster_half).
  * Called after root growth (octree.cpp:151-212). */
 int gpis_rebase(gpis_ctx* ctx, const int32_t* root_min_cell, int levels);
+/* Read the root box back (3 ints + levels): what a replica needs next to the imported records. */
+int gpis_get_rebase(gpis_ctx* ctx, int32_t* root_min_cell, int* levels);
 
 /* Read one trained leaf back (tests / debugging). Any out pointer may be NULL.
  * L is returned dense row-major n x n (lower), as OnGPIS holds it (OnGPIS.h:40-43). Returns n,

@@ -1,0 +1,126 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libgpisref.so, built from
+/root/reference by oracle/Makefile) — run in the build container where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors; these fixtures are outputs of the
+reference's own code on small seeded inputs, and pin the C restatement oracle on machines where
+oracle/_ref cannot be rebuilt. Bundled-data inputs (three laser scans of data/2D/gazebo1.mat) are
+stored next to the outputs so nothing reads /root/reference at test time.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+from oracle import refpy  # noqa: E402
+
+
+def leaf(dim, N, seed):
+    rng = np.random.default_rng(seed)
+    P = H.P3 if dim == 3 else H.P2
+    s = H.leaf_samples3(N, rng) if dim == 3 else H.leaf_samples2(N, rng)
+    g = refpy.RefGP(dim, s, P["scale"], P["noise"])
+    alpha, L, gf = g.factors()
+    sx = np.where(gf > 0, s[:, 2 * dim + 1], 2.0).astype(np.float32)
+    K = refpy.matern_train(dim, s[:, :dim], gf, P["scale"], sx, s[:, 2 * dim + 2])
+    if dim == 3:
+        x = (s[::2, :3] + rng.normal(0, 0.01, s[::2, :3].shape)).astype(np.float32)
+    else:
+        x = (s[::2, :2] + rng.normal(0, 0.3, s[::2, :2].shape)).astype(np.float32)
+    Ks = refpy.matern_test(dim, s[:, :dim], gf, x[:1], P["scale"])
+    rows = g.test(x)
+    return dict(samples=s, gradflag=gf, K=K, alpha=alpha, L=L, x=x, rows=rows, Ks0=Ks)
+
+
+def obs2d(seed):
+    rng = np.random.default_rng(seed)
+    ni, nj = 23, 28
+    v = ((np.arange(ni) * 2 - 20) / 568.0).astype(np.float32)
+    u = ((np.arange(nj) * 2 - 31) / 568.0).astype(np.float32)
+    vu = np.zeros((nj, ni, 2), np.float32)
+    vu[:, :, 0] = v[None, :]
+    vu[:, :, 1] = u[:, None]
+    z = 1.2 + 3.0 * vu[:, :, 0] - 2.0 * vu[:, :, 1] + 0.05 * np.sin(90 * vu[:, :, 1])
+    zinv = (1.0 / z).astype(np.float32)
+    zinv[rng.uniform(size=zinv.shape) < 0.15] = -1.0
+    zinv[:9, :9] = -1.0    # one fully invalid tile
+    o = refpy.RefObs2D()
+    o.train(vu, zinv, ni, nj)
+    bi, bj = o.partition()
+    xt = np.stack([rng.uniform(v[0] - 0.01, v[-1] + 0.01, 96), rng.uniform(u[0] - 0.01, u[-1] + 0.01, 96)], 1).astype(np.float32)
+    val0 = rng.uniform(size=96).astype(np.float32)
+    val, var = o.test(xt, val=val0)
+    return dict(vu=vu.reshape(-1), zinv=zinv.reshape(-1), ni=ni, nj=nj, bi=bi, bj=bj, tiles=o.tiles(), xt=xt, val0=val0, val=val, var=var)
+
+
+def seq2d():
+    import scipy.io
+    m = scipy.io.loadmat("/root/reference/data/2D/gazebo1.mat")
+    thetas = m["thetas"].ravel().astype(np.float32)
+    frames = [100, 200, 300, 400]
+    ranges = m["ranges"][frames].astype(np.float32)
+    poses = m["poses"][frames]
+    pose6 = np.stack([[x, y, np.cos(p), np.sin(p), -np.sin(p), np.cos(p)] for x, y, p in poses]).astype(np.float32)
+    M = refpy.RefMap2()
+    xs = np.arange(-4.8, 12.1, 0.4)
+    ys = np.arange(-12.0, 4.1, 0.4)    # multiples of 0.4: hits lattice planes and exact distance ties
+    xg, yg = np.meshgrid(xs, ys)
+    X = np.stack([xg.ravel(), yg.ravel()], 1).astype(np.float32)
+    out = dict(thetas=thetas, ranges=ranges, pose6=pose6, X=X)
+    for i in range(len(frames)):
+        M.update(thetas, ranges[i], pose6[i])
+        out[f"samples{i}"] = M.all_samples()
+        c, n, tr = M.clusters()
+        out[f"leaves{i}"] = c
+        out[f"leafcount{i}"] = n
+    out["rows"] = M.test(X)
+    out["boxes"] = M.cluster_boxes()
+    # 1-D observation GP on the first scan
+    o = refpy.RefObs1D()
+    f = (1.0 / np.sqrt(ranges[0])).astype(np.float32)
+    o.train(thetas, f)
+    rng = np.random.default_rng(5)
+    xt = rng.uniform(thetas[0] - 0.05, thetas[-1] + 0.05, 128).astype(np.float32)
+    val, var = o.test(xt)
+    out.update(obs1_ranges=o.ranges(), obs1_xt=xt, obs1_val=val, obs1_var=var)
+    return out
+
+
+def map3d(seed):
+    rng = np.random.default_rng(seed)
+    P = H.P3
+    s = H.sphere_samples(0.12, 0.0125, (0.0517, 0.0231, 0.0113), rng)
+    M = refpy.RefMap3()
+    M.insert_samples(s)
+    M.update_gps()
+    centres, offs, samples, trained = H.ref_map_to_csr(M, P)
+    d = rng.normal(size=(300, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    x = (d * (0.12 + rng.uniform(-0.09, 0.09, 300))[:, None] + np.array([0.0517, 0.0231, 0.0113])).astype(np.float32)
+    # lattice-symmetric queries (multiples of 0.025): exact centre-distance ties, > 16 candidates
+    g = np.arange(-0.1, 0.2001, 0.025)
+    xs = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    init = rng.uniform(size=(len(x) + len(xs), 8)).astype(np.float32)
+    X = np.concatenate([x, xs])
+    rows = M.test(X, init.copy())
+    ncand = np.array([M.candidates(q, P["search"])[0].shape[0] for q in X], np.int32)
+    root_c, root_half = M.root()
+    return dict(samples_in=s, centres=centres, offsets=offs, samples=samples, X=X, init=init, rows=rows, ncand=ncand,
+                boxes=M.cluster_boxes(), root_c=root_c, root_half=np.float32(root_half))
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "leaf3d.npz"), **leaf(3, 24, 11))
+    np.savez_compressed(os.path.join(HERE, "leaf2d.npz"), **leaf(2, 18, 12))
+    np.savez_compressed(os.path.join(HERE, "obs2d.npz"), **obs2d(13))
+    np.savez_compressed(os.path.join(HERE, "seq2d.npz"), **seq2d())
+    np.savez_compressed(os.path.join(HERE, "map3d.npz"), **map3d(14))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,4 +1,4 @@
-"""TEST SCAFFOLDING: builds tests/_mock/{libgpis_b200.so, libgpismap_host.so} — the host classes
+"""TEST SCAFFOLDING: builds tests/_mock/{libgpis_mock.so, libgpismap_host_mock.so} — the host classes
 linked against a CPU stand-in of the C ABI that is backed by the oracle — so host logic can be
 checked without a GPU. Never used by the product path."""
 import os
@@ -11,8 +11,8 @@ OUT = os.path.join(HERE, "_mock")
 
 def build():
     os.makedirs(OUT, exist_ok=True)
-    mock = os.path.join(OUT, "libgpis_b200.so")
-    host = os.path.join(OUT, "libgpismap_host.so")
+    mock = os.path.join(OUT, "libgpis_mock.so")   # its own soname: must never alias the real library
+    host = os.path.join(OUT, "libgpismap_host_mock.so")
     srcs_mock = [os.path.join(HERE, "mock_cabi", "mock_gpis.cpp"), os.path.join(ROOT, "oracle", "gpis_oracle.c")]
     hostdir = os.path.join(ROOT, "gpismap_b200", "host")
     srcs_host = [os.path.join(hostdir, f) for f in sorted(os.listdir(hostdir)) if f.endswith(".cpp")]
@@ -29,7 +29,7 @@ def build():
                            "-o", mock, srcs_mock[0], obj, "-lm"])
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
                            "-I" + os.path.join(ROOT, "include"), "-I" + hostdir, "-o", host] + srcs_host +
-                          ["-L" + OUT, "-lgpis_b200", "-Wl,-rpath,$ORIGIN"])
+                          ["-L" + OUT, "-lgpis_mock", "-Wl,-rpath,$ORIGIN"])
     return host
 
 
