@@ -350,9 +350,10 @@ def cpu_baseline(args, gmap, X):
         from gpismap_b200 import synth
         cores = refpy.lib().ref_hardware_concurrency()
         S = gmap.all_samples()
-        # sub-box: a corner region of the room holding two walls and the floor
-        lo = np.array([synth.ROOM_HI[0] - 0.55, synth.ROOM_LO[1] - 0.1, synth.ROOM_LO[2] - 0.1])
-        hi = np.array([synth.ROOM_HI[0] + 0.1, synth.ROOM_LO[1] + 0.55, synth.ROOM_LO[2] + 0.55])
+        # sub-box: 0.6 m cube around the wall/floor edge nearest to a well-observed sample
+        p0 = S[len(S) // 2, :3].astype(np.float64)
+        lo = p0 - 0.3
+        hi = p0 + 0.3
         m = 0.2
         sel = np.all((S[:, :3] > lo - m) & (S[:, :3] < hi + m), axis=1)
         M = refpy.RefMap3()

@@ -20,6 +20,7 @@
 #include "obs_gp.cuh"
 #include "query.cuh"
 #include "query_v2.cuh"
+#include "query_v3.cuh"
 
 using namespace gpis;
 
@@ -157,7 +158,7 @@ struct gpis_ctx {
     std::vector<uint64_t> dirty_keys;
     void* d_export = nullptr; uint64_t export_cap = 0;
     gpis_stats st{};
-    int eval_version = 2;
+    int eval_version = 3;
 };
 
 #define CK(call)                                                                                   \
@@ -352,7 +353,7 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
     if (rc) return rc;
     CK(cudaFuncSetAttribute(k_leaf_train, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_eval_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    rc = query_v2_init(ctx->err);
+    rc = query_eval_init(ctx->err);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return GPIS_OK;
@@ -702,12 +703,9 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
             if (npairs > 0) {
                 CK(cudaEventRecord(ctx->ev[2], ctx->stream));
                 {
-                    // v2 keeps the right-hand sides of 8 queries in shared memory: nb <= 40 (n <= 1280)
-                    const bool use_v1 = ctx->eval_version == 1 || Eval2Smem::total(ctx->max_nb) > 227 * 1024;
-                    const int smem1 = (1 + dim) * ctx->max_nb * 32 * (int)sizeof(float);
-                    int rc = query_v2_eval(ctx->stream, xq, ctx->T, ctx->qp, W, npairs, ctx->slot_count, ctx->max_nb,
-                                           &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err, ctx->d_acc,
-                                           use_v1, smem1);
+                    int rc = query_eval(ctx->stream, xq, ctx->T, ctx->qp, W, npairs, ctx->slot_count, ctx->max_nb,
+                                        &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err, ctx->d_acc,
+                                        ctx->eval_version);
                     if (rc) return rc;
                 }
                 CK(cudaGetLastError());
@@ -942,6 +940,10 @@ int gpis_export_dirty(gpis_ctx* ctx, const void** buf_device, uint64_t* bytes) {
     for (uint64_t k : keys) {
         const HostLeaf& hl = ctx->leaves[k];
         CK(cudaMemcpyAsync((unsigned char*)ctx->d_export + off, (const void*)hl.rec, hl.rec_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        // the candidate box may have been overridden after training (gpis_leaves_set_boxes): ship the current one
+        float box[8] = {hl.lo[0], hl.lo[1], hl.lo[2], 0.f, hl.hi[0], hl.hi[1], hl.hi[2], 0.f};
+        CK(cudaMemcpyAsync((unsigned char*)ctx->d_export + off + offsetof(LeafHeader, lo), box, sizeof(box), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `box` is a stack buffer
         off += align_up(hl.rec_bytes, 256);
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1004,7 +1006,7 @@ int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out) {
 }
 
 int gpis_set_eval_version(gpis_ctx* ctx, int v) {
-    if (!ctx || (v != 1 && v != 2)) return GPIS_ERR_ARG;
+    if (!ctx || v < 1 || v > 3) return GPIS_ERR_ARG;
     ctx->eval_version = v;
     return GPIS_OK;
 }

@@ -255,9 +255,9 @@ k_select2(int64_t nq, const float* __restrict__ res, LeafTable T, QueryParams P,
 // Straightforward blocked forward substitution that streams the leaf's tiles from L2.
 #define EVAL1_THREADS 128
 __global__ void __launch_bounds__(EVAL1_THREADS)
-k_eval_v1(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, int pair_begin) {
+k_eval_v1(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, const int2* __restrict__ pairs) {
     extern __shared__ __align__(16) float sm[];
-    const int2 pr = W.pairs[pair_begin + blockIdx.x];
+    const int2 pr = pairs[blockIdx.x];
     const int q = pr.x, rank = (pr.y >> 28) & 3, slot = pr.y & 0x0fffffff;
     const int dim = P.dim, w = 1 + dim;
     const unsigned char* rec = reinterpret_cast<const unsigned char*>(T.rec[slot]);

@@ -32,8 +32,10 @@ struct SortBufs {
     int32_t* istart;   // nslots + 1   (exclusive prefix of ceil(count/QB))
     int32_t* cursor;   // nslots
     int2* sorted;      // npairs
-    int4* items;       // work items: slot, first sorted pair, count, unused
-    int32_t* totals;   // [0] = number of items
+    int4* items;       // work items of the 8-query class: slot, first sorted pair, count, unused
+    int4* itemsB;      // work items of the 4-query class (leaves too large for 32 right-hand sides in smem)
+    int2* pairsC;      // pairs of leaves too large for either (one CTA per pair, k_eval_v1)
+    int32_t* totals;   // [0] = #items (legacy list), [1] = #itemsA, [2] = #itemsB, [3] = #pairsC
 };
 
 __global__ void k_pair_hist(const int2* __restrict__ pairs, int npairs, int32_t* __restrict__ count) {
@@ -81,6 +83,26 @@ __global__ void k_make_items(SortBufs S, int nslots) {
     if (c == 0) return;
     int it = S.istart[s];
     for (int o = 0; o < c; o += QB) S.items[it++] = make_int4(s, S.start[s] + o, min(QB, c - o), 0);
+}
+
+// Work lists by leaf size class (nb = 32-row blocks of the leaf system). A leaf's items are contiguous so that
+// CTAs running at the same time share its tiles in L2.
+__global__ void k_make_items_classed(SortBufs S, LeafTable T, int nslots, int nbA, int nbB) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const int c = S.count[s];
+    if (c == 0) return;
+    const int nb = T.meta[s].w;
+    if (nb <= nbA) {
+        int it = atomicAdd(&S.totals[1], (c + 7) / 8);
+        for (int o = 0; o < c; o += 8) S.items[it++] = make_int4(s, S.start[s] + o, min(8, c - o), 0);
+    } else if (nb <= nbB) {
+        int it = atomicAdd(&S.totals[2], (c + 3) / 4);
+        for (int o = 0; o < c; o += 4) S.itemsB[it++] = make_int4(s, S.start[s] + o, min(4, c - o), 0);
+    } else {
+        int it = atomicAdd(&S.totals[3], c);
+        for (int o = 0; o < c; ++o) S.pairsC[it++] = S.sorted[S.start[s] + o];
+    }
 }
 
 // Algorithmic work of one evaluation pass, accumulated over leaves with work:
@@ -296,67 +318,6 @@ k_eval_v2(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + w + c] = (float)(prior - (double)s);
         }
     }
-}
-
-// ------------------------------------------------------------------ host side
-static inline int query_v2_init(std::string& err) {
-    cudaError_t e = cudaFuncSetAttribute(k_eval_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(k_eval_v2): ") + cudaGetErrorString(e); return -2; }
-    return 0;
-}
-
-// Buckets the npairs work items in W.pairs by leaf and evaluates them. *d_sort is a grow-only
-// device buffer owned by the context.
-static inline int query_v2_eval(cudaStream_t st, const float* d_x, const LeafTable& T, const QueryParams& P,
-                                const QueryWork& W, int npairs, int nslots, int max_nb, int32_t** d_sort,
-                                int64_t* sort_cap, int64_t* launches, std::string& err, double* d_acc, bool use_v1,
-                                int v1_smem) {
-#define CK2(call)                                                                 \
-    do {                                                                          \
-        cudaError_t e_ = (call);                                                  \
-        if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return -2; } \
-    } while (0)
-    const int64_t max_items = npairs / QB + nslots + 1;
-    const int64_t need = (int64_t)nslots * 4 + 8 + (int64_t)npairs * 2 + max_items * 4 + 64;
-    if (*sort_cap < need) {
-        if (*d_sort) CK2(cudaFree(*d_sort));
-        *d_sort = nullptr; *sort_cap = 0;
-        CK2(cudaMalloc(d_sort, sizeof(int32_t) * (need + need / 4)));
-        *sort_cap = need + need / 4;
-    }
-    SortBufs S;
-    int32_t* p = *d_sort;
-    S.totals = p; p += 16;
-    S.count = p; p += nslots;
-    S.start = p; p += nslots + 1;
-    S.istart = p; p += nslots + 1;
-    S.cursor = p; p += nslots;
-    p += ((uintptr_t)p & 15) ? (4 - (((uintptr_t)p >> 2) & 3)) : 0;   // 16-byte align for int4
-    S.items = reinterpret_cast<int4*>(p); p += max_items * 4;
-    S.sorted = reinterpret_cast<int2*>(p);
-    CK2(cudaMemsetAsync(S.count, 0, sizeof(int32_t) * nslots, st));
-    k_pair_hist<<<(npairs + 255) / 256, 256, 0, st>>>(W.pairs, npairs, S.count);
-    k_slot_scan<<<1, 1024, 0, st>>>(S, nslots);
-    k_pair_scatter<<<(npairs + 255) / 256, 256, 0, st>>>(W.pairs, npairs, S);
-    k_make_items<<<(nslots + 255) / 256, 256, 0, st>>>(S, nslots);
-    if (d_acc) { k_query_stats<<<(nslots + 255) / 256, 256, 0, st>>>(S, T, nslots, d_acc); *launches += 1; }
-    *launches += 4;
-    if (use_v1) {   // reference-style one CTA per (query, leaf) pair; kept for leaves too large for v2's shared memory
-        k_eval_v1<<<npairs, EVAL1_THREADS, v1_smem, st>>>(d_x, T, P, W, 0);
-        *launches += 1;
-        CK2(cudaGetLastError());
-        return 0;
-    }
-    int32_t nitems = 0;
-    CK2(cudaMemcpyAsync(&nitems, S.totals, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CK2(cudaStreamSynchronize(st));
-    if (nitems > 0) {
-        k_eval_v2<<<nitems, EVAL2_THREADS, Eval2Smem::total(max_nb), st>>>(d_x, T, P, W, S);
-        *launches += 1;
-        CK2(cudaGetLastError());
-    }
-#undef CK2
-    return 0;
 }
 
 }  // namespace gpis

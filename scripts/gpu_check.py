@@ -129,7 +129,7 @@ def map_parity(dim):
     print(f"  ref test {nq/(t1-t0):.0f} q/s; oracle vs ref max abs {np.abs(ores-want).max():.2e}; ties {int(otie.sum())}")
     slot_of = np.array([ctx.leaf_index(c) for c in cells])
     inv = -np.ones(slot_of.max() + 2, np.int64); inv[slot_of] = np.arange(len(slot_of))
-    for ver in (1, 2):
+    for ver in (1, 2, 3):
         ctx.set_eval_version(ver)
         t0 = time.time(); got, chosen, tie = ctx.query(x, init.copy(), debug=True); t1 = time.time()
         stq = ctx.stats()

@@ -95,7 +95,7 @@ def _fixture_map(cabi):
     return ctx, g, cells, P
 
 
-@pytest.mark.parametrize("version", [2, 1])
+@pytest.mark.parametrize("version", [3, 2, 1])
 def test_query_matches_reference_fixture(cabi, oracle, oracle64, version):
     """K3 + K4 against rows produced by the unmodified reference (tests/golden/map3d.npz): candidate
     counts bit-exact (incl. lattice-touching boxes), picks identical where the fixture has exact ties
@@ -147,6 +147,38 @@ def test_query_invariances(cabi):
     v1 = ctx.query(X)
     ev = base[:, 4] < 1.0
     assert np.abs(v1[ev, 0] - base[ev, 0]).max() < 2e-5
+    ctx.close()
+
+
+def test_query_large_leaves(cabi, oracle, oracle64):
+    """Leaf systems beyond the 8-query kernel's shared-memory budget: n ~ 1400 runs the 4-query variant,
+    n ~ 2700 the one-CTA-per-pair kernel; both against the oracle."""
+    rng = np.random.default_rng(9)
+    P = H.P3
+    ctx = cabi.Ctx(3)
+    cells = np.array([[3, 1, -2], [9, 1, -2], [15, 1, -2]], np.int32)
+    centres = ((2 * cells + 1) * np.float64(np.float32(P["half"]))).astype(np.float32)
+    sizes = [120, 360, 690]
+    offs, chunks = [0], []
+    for c, N in zip(centres, sizes):
+        s = H.leaf_samples3(N, rng, spread=0.045)
+        s[:, :3] += c - np.array([0.3125, -0.1375, 0.0625], np.float32)
+        s[:, 8] = rng.uniform(0.01, 0.08, N)
+        chunks.append(s)
+        offs.append(offs[-1] + N)
+    samples = np.concatenate(chunks)
+    st = ctx.leaves_update(cells, centres, offs, samples)
+    assert (st == 0).all()
+    ns = [ctx.leaf_get(c, want_L=False)["n"] for c in cells]
+    assert ns[1] > 1280 and ns[2] > 2560
+    x = np.concatenate([c + rng.uniform(-0.02, 0.02, (40, 3)) for c in centres]).astype(np.float32)
+    got = ctx.query(x)
+    order = np.argsort(cells[:, 0])     # same y, z: DFS order = x ascending
+    gps = [oracle.gp_train(3, chunks[i], P["scale"], P["noise"]) for i in order]
+    gps64 = [oracle64.gp_train(3, chunks[i], P["scale"], P["noise"]) for i in order]
+    want = oracle.make_map(3, centres[order], P["half"], gps, P["search"], P["var_thre"], P["noise"]).test(x)
+    want64 = oracle64.make_map(3, centres[order], P["half"], gps64, P["search"], P["var_thre"], P["noise"]).test(x)
+    H.check_rows(got, want, want64, 3, label="large leaves")
     ctx.close()
 
 
@@ -230,13 +262,15 @@ def test_gpismap3_synthetic_frames(cabi, oracle):
     S = m.all_samples()
     nrm = np.linalg.norm(S[:, 3:6], axis=1)
     assert np.median(np.abs(nrm - 1)) < 1e-3                      # unit normals from evalPoints
-    X = synth.query_grid(40)
+    rng = np.random.default_rng(3)
+    X = (S[::40, :3] - S[::40, 3:6] * rng.uniform(0.002, 0.02, (len(S[::40]), 1))).astype(np.float32)   # 2..20 mm inside the room
     rows = m.test(X)
-    ev = rows[:, 4] < 0.5
-    assert ev.sum() > 1000
-    # SDF sanity: f + fbias ~ signed distance to the nearest wall for confident queries
+    ev = rows[:, 4] < 0.3
+    assert ev.sum() > 0.5 * len(X)
+    # SDF sanity: f + fbias ~ distance to the nearest wall for confident queries (sign convention of the
+    # reference: the field decreases along the stored normal)
     d = np.minimum(X - synth.ROOM_LO, synth.ROOM_HI - X).min(1)
-    assert np.abs((rows[ev, 0] + 0.2) - d[ev]).max() < 0.03
+    assert np.median(np.abs(np.abs(rows[ev, 0] + 0.2) - d[ev])) < 0.004
     m.reset()
     assert m.getAllPoints().shape[0] == 0 and m.test(X) is None
     m.close()
