@@ -106,14 +106,73 @@ struct QueryParams {
     int levels;
 };
 
+// ------------------------------------------------------------------ exp in double-float arithmetic
+// The reference evaluates exp() in double and rounds the final product to float (covFnc.cpp:29-33, SURVEY
+// §3.3). B200's vector FP64 rate is a small fraction of its FP32 rate (profiles/r01: the double exp made the
+// covariance build the longest phase of leaf training), so exp and the products are carried out in
+// double-float (hi + lo, ~48 significant bits) on the FP32 pipe instead: error-free transforms with explicit
+// FMAs, relative error < 1e-11 (scripts/dfexp_check.py), which rounds to the same float as the double path
+// except when the exact value lies within ~2^-36 of a rounding boundary.
+struct DF { float hi, lo; };
+__device__ __forceinline__ DF df_two_sum(float a, float b) {
+    const float s = a + b, bb = s - a;
+    return DF{s, (a - (s - bb)) + (b - bb)};
+}
+__device__ __forceinline__ DF df_fast_two_sum(float a, float b) {   // |a| >= |b|
+    const float s = a + b;
+    return DF{s, b - (s - a)};
+}
+__device__ __forceinline__ DF df_mul(DF x, DF y) {
+    const float p = x.hi * y.hi;
+    float e = __fmaf_rn(x.hi, y.hi, -p);
+    e = e + (x.hi * y.lo + x.lo * y.hi);
+    return df_fast_two_sum(p, e);
+}
+__device__ __forceinline__ DF df_add(DF x, DF y) {
+    DF s = df_two_sum(x.hi, y.hi);
+    return df_fast_two_sum(s.hi, s.lo + (x.lo + y.lo));
+}
+// exp(x) for a float x in [-80, 0.4]: x = k ln2 + r, |r| <= 0.35; Taylor through r^5 in double-float, tail in float
+__device__ __forceinline__ DF exp_df(float x) {
+    const float k = rintf(x * 1.44269504f);
+    const float LN2_HI = 0.693145751953125f;        // 0x1.62e4p-1: k * LN2_HI is exact for |k| < 2^9
+    const float LN2_MID = 1.42860677e-06f;          // 0x1.7f7d1cp-20
+    const float LN2_LO = 5.49560397e-14f;           // ln2 - LN2_HI - LN2_MID
+    const float r1 = __fmaf_rn(-k, LN2_HI, x);
+    const float p = k * LN2_MID, pe = __fmaf_rn(k, LN2_MID, -p);
+    DF r = df_two_sum(r1, -p);
+    r = df_fast_two_sum(r.hi, r.lo - (pe + k * LN2_LO));
+    const float t = __fmaf_rn(__fmaf_rn(__fmaf_rn(2.75573192e-06f, r.hi, 2.48015873e-05f), r.hi, 1.98412698e-04f), r.hi, 1.38888889e-03f);
+    DF u = df_two_sum(8.33333377e-03f, r.hi * t);   // 1/120 = 0x1.111112p-7 - 0x1.dddddep-32
+    u.lo += -4.34617203e-10f;
+    u = df_add(df_mul(u, r), DF{4.16666679e-02f, -1.24176347e-09f});   // 1/24
+    u = df_add(df_mul(u, r), DF{1.66666672e-01f, -4.96705388e-09f});   // 1/6
+    u = df_add(df_mul(u, r), DF{0.5f, 0.f});
+    u = df_add(df_mul(u, r), DF{1.0f, 0.f});
+    u = df_add(df_mul(u, r), DF{1.0f, 0.f});
+    const float sc = __int_as_float(((int)k + 127) << 23);   // 2^k, exact scaling
+    return DF{u.hi * sc, u.lo * sc};
+}
+__device__ __forceinline__ float df_round(DF v) { return v.hi + v.lo; }
+// (float)((double)c * e)
+__device__ __forceinline__ float df_mulf_round(float c, DF e) {
+    const float p = e.hi * c;
+    float err = __fmaf_rn(e.hi, c, -p);
+    err = __fmaf_rn(e.lo, c, err);
+    return p + err;
+}
+
 // ------------------------------------------------------------------ Matern-3/2 pieces
-// Same mixed precision as the reference (covFnc.cpp:29-33 with SURVEY §3.3): products in float,
-// exp and the final product in double, rounded once to float. -fmad=false keeps the float
-// products unfused like the reference's SSE2 build.
-__device__ __forceinline__ float kf_val(float r, float a, double e) { return (float)((1.0 + (double)(a * r)) * e); }
-__device__ __forceinline__ float kf1_val(float dx, float a, double e) { return (float)((double)(a * a * dx) * e); }
-__device__ __forceinline__ float kf2_val(float r, float dx1, float dx2, float delta, float a, double e) {
-    return (float)((double)(a * a * (delta - a * dx1 * dx2 / r)) * e);
+// Same mixed precision as the reference (covFnc.cpp:29-33 with SURVEY §3.3): products in float, exp and the
+// final product beyond float precision, rounded once to float. -fmad=false keeps the float products unfused
+// like the reference's SSE2 build. e = exp_df(-a*r).
+__device__ __forceinline__ float kf_val(float r, float a, DF e) {
+    const DF s = df_two_sum(1.0f, a * r);          // 1.0 + (double)(a*r), exact
+    return df_round(df_mul(s, e));
+}
+__device__ __forceinline__ float kf1_val(float dx, float a, DF e) { return df_mulf_round(a * a * dx, e); }
+__device__ __forceinline__ float kf2_val(float r, float dx1, float dx2, float delta, float a, DF e) {
+    return df_mulf_round(a * a * (delta - a * dx1 * dx2 / r), e);
 }
 
 // ------------------------------------------------------------------ PTX helpers (TMA bulk copy)
@@ -123,6 +182,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(

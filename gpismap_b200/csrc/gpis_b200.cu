@@ -1005,6 +1005,15 @@ int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out) {
     return GPIS_OK;
 }
 
+#ifdef E3_TIMING
+int gpis_debug_timing(long long* out) {   // 64 warps x 16 counters of the instrumented CTA, then reset
+    cudaMemcpyFromSymbol(out, g_e3_timing, sizeof(long long) * 64 * 16);
+    static long long zeros[64 * 16];
+    cudaMemcpyToSymbol(g_e3_timing, zeros, sizeof(zeros));
+    return 0;
+}
+#endif
+
 int gpis_set_eval_version(gpis_ctx* ctx, int v) {
     if (!ctx || v < 1 || v > 3) return GPIS_ERR_ARG;
     ctx->eval_version = v;

@@ -275,7 +275,7 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
                     s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c];
                 }
                 const float r = sqrtf(s2);
-                const double e = exp((double)(-P.a * r));
+                const DF e = exp_df(-P.a * r);
                 // value(a) - value(b)
                 if (a0 > b) KSTORE(a0, b, kf_val(r, P.a, e));
                 if (ga >= 0) {

@@ -84,7 +84,7 @@ k_obs_train(const float* __restrict__ xin, const float* __restrict__ fin, const 
                 float s2 = 0.f;
                 for (int c = 0; c < P.d; ++c) { const float dd = xs[t * P.d + c] - xs[j * P.d + c]; s2 = (c == 0) ? dd * dd : s2 + dd * dd; }
                 // the reference computes the (k<j) entry and mirrors it; |d| is symmetric so both agree
-                v = (float)exp((double)(-P.a * sqrtf(s2)));
+                v = df_round(exp_df(-P.a * sqrtf(s2)));
             }
             Ks[t * (OBS_MAXP + 1) + j] = v;
         }
@@ -165,7 +165,7 @@ k_obs_test(const float* __restrict__ xt, int m, const float* __restrict__ b0, co
             const float d0 = T->x[i * P.d] - x0;
             s2 = d0 * d0;
             if (P.d == 2) { const float d1 = T->x[i * P.d + 1] - x1; s2 = s2 + d1 * d1; }
-            k[h] = (float)exp((double)(-P.a * sqrtf(s2)));
+            k[h] = df_round(exp_df(-P.a * sqrtf(s2)));
         }
     }
     float f = 0.f;

@@ -283,7 +283,7 @@ k_eval_v1(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         float d[3], s2 = 0.f;
         for (int c = 0; c < dim; ++c) { d[c] = xs[c] - xq[c]; s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c]; }
         const float r = sqrtf(s2);
-        const double e = exp((double)(-P.a * r));
+        const DF e = exp_df(-P.a * r);
         Ks[k] = kf_val(r, P.a, e);
         float k1[3];
         for (int c = 0; c < dim; ++c) { k1[c] = kf1_val(d[c], P.a, e); Ks[(1 + c) * npad + k] = k1[c]; }

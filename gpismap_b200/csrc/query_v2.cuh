@@ -34,8 +34,9 @@ struct SortBufs {
     int2* sorted;      // npairs
     int4* items;       // work items of the 8-query class: slot, first sorted pair, count, unused
     int4* itemsB;      // work items of the 4-query class (leaves too large for 32 right-hand sides in smem)
+    int4* itemsM;      // work items of the 6-query class
     int2* pairsC;      // pairs of leaves too large for either (one CTA per pair, k_eval_v1)
-    int32_t* totals;   // [0] = #items (legacy list), [1] = #itemsA, [2] = #itemsB, [3] = #pairsC
+    int32_t* totals;   // [0] = #items (legacy list), [1] = #itemsA, [2] = #itemsB, [3] = #pairsC, [4] = #itemsM
 };
 
 __global__ void k_pair_hist(const int2* __restrict__ pairs, int npairs, int32_t* __restrict__ count) {
@@ -87,7 +88,7 @@ __global__ void k_make_items(SortBufs S, int nslots) {
 
 // Work lists by leaf size class (nb = 32-row blocks of the leaf system). A leaf's items are contiguous so that
 // CTAs running at the same time share its tiles in L2.
-__global__ void k_make_items_classed(SortBufs S, LeafTable T, int nslots, int nbA, int nbB) {
+__global__ void k_make_items_classed(SortBufs S, LeafTable T, int nslots, int nbA, int nbM, int nbB) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     const int c = S.count[s];
@@ -96,6 +97,9 @@ __global__ void k_make_items_classed(SortBufs S, LeafTable T, int nslots, int nb
     if (nb <= nbA) {
         int it = atomicAdd(&S.totals[1], (c + 7) / 8);
         for (int o = 0; o < c; o += 8) S.items[it++] = make_int4(s, S.start[s] + o, min(8, c - o), 0);
+    } else if (nb <= nbM) {
+        int it = atomicAdd(&S.totals[4], (c + 5) / 6);
+        for (int o = 0; o < c; o += 6) S.itemsM[it++] = make_int4(s, S.start[s] + o, min(6, c - o), 0);
     } else if (nb <= nbB) {
         int it = atomicAdd(&S.totals[2], (c + 3) / 4);
         for (int o = 0; o < c; o += 4) S.itemsB[it++] = make_int4(s, S.start[s] + o, min(4, c - o), 0);
@@ -198,7 +202,7 @@ k_eval_v2(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         float d[3], s2 = 0.f;
         for (int c = 0; c < dim; ++c) { d[c] = xs[c] - xq[c]; s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c]; }
         const float r = sqrtf(s2);
-        const double e = exp((double)(-P.a * r));
+        const DF e = exp_df(-P.a * r);
         float* col = U + 4 * qi;
         col[k * 32] = kf_val(r, P.a, e);
         float k1[3];

@@ -23,34 +23,66 @@
 
 namespace gpis {
 
+#ifndef E3_WARPS
 #define E3_WARPS 8
-#define E3_THREADS (E3_WARPS * 32)
+#endif
+#ifndef E3_R
 #define E3_R 4                      // block rows per warp per wave
-#define E3_WAVE (E3_WARPS * E3_R)   // 32 block rows per wave
+#endif
+#define E3_THREADS (E3_WARPS * 32)
+#define E3_WAVE (E3_WARPS * E3_R)   // block rows per wave
+#define E3_STAGE_FLOATS (E3_R * 256)   // one stage: E3_R quarter tiles of 1 KB
 
 struct Eval3Smem {
     static constexpr int off_bar = 0;                                // per warp 2 mbarriers
     static constexpr int off_stage = 256;                            // per warp 2 stages x 4 slots x 1 KB
-    static constexpr int off_red = off_stage + E3_WARPS * 2 * 4096;  // E3_WARPS x 32 floats
-    static constexpr int off_U = off_red + E3_WARPS * 32 * 4;
+    static constexpr int off_red = off_stage + E3_WARPS * 2 * E3_STAGE_FLOATS * 4;  // E3_WARPS x 32 floats
+    static constexpr int off_ready = off_red + E3_WARPS * 32 * 4;     // one mbarrier per block row (<= 128)
+    static constexpr int off_U = off_ready + 1024;
     static int total(int nbmax, int ncol) { return off_U + nbmax * 32 * ncol * 4; }
 };
 
-// acc[r][i][j] -= sum_{k<8} A_r[k][4rg+i] * B[k][CPL*cg+j] for r in [R0, R0+R);  A_r: quarter tile [8][32] at
-// As + r*256, B: [8][NCOL] rows of U. R0 and R are compile-time so the accumulators stay in registers.
-template <int R0, int R, int CPL, int NCOL>
+// CPL consecutive floats <-> registers: 16-byte accesses when CPL is a multiple of 4, 8-byte otherwise
+template <int CPL>
+__device__ __forceinline__ void ld_cols(const float* __restrict__ p, float (&v)[CPL]) {
+    if constexpr (CPL % 4 == 0) {
+#pragma unroll
+        for (int t = 0; t < CPL / 4; ++t) {
+            const float4 b = *reinterpret_cast<const float4*>(p + 4 * t);
+            v[4 * t] = b.x; v[4 * t + 1] = b.y; v[4 * t + 2] = b.z; v[4 * t + 3] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < CPL / 2; ++t) {
+            const float2 b = *reinterpret_cast<const float2*>(p + 2 * t);
+            v[2 * t] = b.x; v[2 * t + 1] = b.y;
+        }
+    }
+}
+template <int CPL>
+__device__ __forceinline__ void st_cols(float* __restrict__ p, const float (&v)[CPL]) {
+    if constexpr (CPL % 4 == 0) {
+#pragma unroll
+        for (int t = 0; t < CPL / 4; ++t) *reinterpret_cast<float4*>(p + 4 * t) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+    } else {
+#pragma unroll
+        for (int t = 0; t < CPL / 2; ++t) *reinterpret_cast<float2*>(p + 2 * t) = make_float2(v[2 * t], v[2 * t + 1]);
+    }
+}
+
+// acc[s][i][j] -= sum_{k<8} A_s[k][4rg+i] * B[k][CPL*cg+j] for accumulator slots s < R;  A_s: quarter tile
+// [8][32] at As + s*256, B: [8][NCOL] rows of U. Slots are ordered from the warp's LAST block row of the
+// wave upwards, so the rows still active at a column are always a prefix and R is the only variant.
+// k is unrolled by 2 only: the four variants together must stay inside the instruction cache.
+template <int R, int CPL, int NCOL>
 __device__ __forceinline__ void qmma_sub(float (&acc)[E3_R][4][CPL], const float* __restrict__ As,
                                          const float* __restrict__ Bq, int rg, int cg) {
-#pragma unroll
+#pragma unroll 2
     for (int k = 0; k < 8; ++k) {
         float bv[CPL];
+        ld_cols<CPL>(Bq + k * NCOL + CPL * cg, bv);
 #pragma unroll
-        for (int v = 0; v < CPL / 4; ++v) {
-            const float4 b = *reinterpret_cast<const float4*>(Bq + k * NCOL + CPL * cg + 4 * v);
-            bv[4 * v] = b.x; bv[4 * v + 1] = b.y; bv[4 * v + 2] = b.z; bv[4 * v + 3] = b.w;
-        }
-#pragma unroll
-        for (int r = R0; r < R0 + R; ++r) {
+        for (int r = 0; r < R; ++r) {
             const float4 a = *reinterpret_cast<const float4*>(As + r * 256 + k * 32 + 4 * rg);
             const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -60,24 +92,62 @@ __device__ __forceinline__ void qmma_sub(float (&acc)[E3_R][4][CPL], const float
         }
     }
 }
-// rows r0 .. R-1 of this warp are active (a suffix): dispatch to the compile-time variant
+// one accumulator slot S only (the lookahead part of a split visit)
+template <int S, int CPL, int NCOL>
+__device__ __forceinline__ void qmma_one(float (&acc)[E3_R][4][CPL], const float* __restrict__ As,
+                                         const float* __restrict__ Bq, int rg, int cg) {
+#pragma unroll 2
+    for (int k = 0; k < 8; ++k) {
+        float bv[CPL];
+        ld_cols<CPL>(Bq + k * NCOL + CPL * cg, bv);
+        const float4 a = *reinterpret_cast<const float4*>(As + S * 256 + k * 32 + 4 * rg);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) acc[S][i][j] = fmaf(-av[i], bv[j], acc[S][i][j]);
+    }
+}
 template <int CPL, int NCOL>
-__device__ __forceinline__ void qmma_dispatch(int r0, int R, float (&acc)[E3_R][4][CPL], const float* As, const float* Bq, int rg, int cg) {
-    const int code = r0 * 8 + (R - r0);
-    switch (code) {
-        case 0 * 8 + 4: qmma_sub<0, 4, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 0 * 8 + 3: qmma_sub<0, 3, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 0 * 8 + 2: qmma_sub<0, 2, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 0 * 8 + 1: qmma_sub<0, 1, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 1 * 8 + 3: qmma_sub<1, 3, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 1 * 8 + 2: qmma_sub<1, 2, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 1 * 8 + 1: qmma_sub<1, 1, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 2 * 8 + 2: qmma_sub<2, 2, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 2 * 8 + 1: qmma_sub<2, 1, CPL, NCOL>(acc, As, Bq, rg, cg); break;
-        case 3 * 8 + 1: qmma_sub<3, 1, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+__device__ __forceinline__ void qmma_dispatch_one(int slot, float (&acc)[E3_R][4][CPL], const float* As, const float* Bq, int rg, int cg) {
+    switch (slot) {
+#if E3_R >= 4
+        case 3: qmma_one<3, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+#endif
+#if E3_R >= 3
+        case 2: qmma_one<2, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+#endif
+#if E3_R >= 2
+        case 1: qmma_one<1, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+#endif
+        default: qmma_one<0, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+    }
+}
+template <int CPL, int NCOL>
+__device__ __forceinline__ void qmma_dispatch(int nact, float (&acc)[E3_R][4][CPL], const float* As, const float* Bq, int rg, int cg) {
+    switch (nact) {
+#if E3_R >= 4
+        case 4: qmma_sub<4, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+#endif
+#if E3_R >= 3
+        case 3: qmma_sub<3, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+#endif
+#if E3_R >= 2
+        case 2: qmma_sub<2, CPL, NCOL>(acc, As, Bq, rg, cg); break;
+#endif
+        case 1: qmma_sub<1, CPL, NCOL>(acc, As, Bq, rg, cg); break;
         default: break;
     }
 }
+
+#ifdef E3_TIMING
+__device__ long long g_e3_timing[64 * 16];   // [warp][phase] accumulated clock64 ticks of blockIdx.x == E3_TIMING
+#define E3_T(var) const long long var = clock64();
+#define E3_ACC(slot, t0, t1) if (blockIdx.x == E3_TIMING && lane == 0) g_e3_timing[warp * 16 + (slot)] += (t1) - (t0);
+#else
+#define E3_T(var)
+#define E3_ACC(slot, t0, t1)
+#endif
 
 template <int QBT>
 __global__ void __launch_bounds__(E3_THREADS, 1)
@@ -100,32 +170,52 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     const int rg = lane >> 2, cg = lane & 3;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + Eval3Smem::off_bar) + warp * 2;
-    float* stg = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_stage) + warp * 2048;   // [2][4][256]
+    float* stg = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_stage) + warp * 2 * E3_STAGE_FLOATS;   // [2][E3_R][256]
     float* red = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_red);
     float* U = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_U);                       // [npad][NCOL]
+    uint64_t* ready = reinterpret_cast<uint64_t*>(smem_raw + Eval3Smem::off_ready);  // mbarrier per block row: U_j final
 
     if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    E3_T(t_begin)
 
     // ---- right-hand sides: k* of every query of the item (covFnc.cpp:282-311 / 425-446)
     {
         float4* U4 = reinterpret_cast<float4*>(U);
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = tid; i < npad * NCOL / 4; i += E3_THREADS) U4[i] = z4;
+        for (int i = tid; i < nb; i += E3_THREADS) mbar_init(&ready[i], 1);
+        fence_mbar_init();
+    }
+    // The tile staging area is idle until the elimination starts: park the leaf's points, alpha and the
+    // query coordinates there (coalesced loads once, instead of a dependent global load per work item).
+    float* stage_all = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_stage);
+    constexpr int kStageFloats = E3_WARPS * 2 * E3_STAGE_FLOATS;
+    const bool park = (N * 4 + npad + 4 * QBT) <= kStageFloats;
+    float4* s_pts = reinterpret_cast<float4*>(stage_all);
+    float* s_alpha = stage_all + N * 4;
+    float* s_xq = s_alpha + npad;
+    if (park) {
+        for (int i = tid; i < N; i += E3_THREADS) s_pts[i] = pts[i];
+        for (int i = tid; i < npad; i += E3_THREADS) s_alpha[i] = alpha[i];
+    }
+    if (tid < cnt * 4) {
+        const int qi = tid >> 2, c = tid & 3;
+        const int q = S.sorted[first + qi].x;
+        (park ? s_xq : red)[tid] = (c < dim) ? x[(int64_t)q * dim + c] : 0.f;
     }
     __syncthreads();
+    const float* xq_s = park ? s_xq : red;
     for (int idx = tid; idx < N * QBT; idx += E3_THREADS) {
         const int qi = idx % QBT, k = idx / QBT;
         if (qi >= cnt) continue;
-        const int q = S.sorted[first + qi].x;
-        float xq[3] = {0.f, 0.f, 0.f};
-        for (int c = 0; c < dim; ++c) xq[c] = x[(int64_t)q * dim + c];
-        const float4 p = pts[k];
+        float xq[3] = {xq_s[4 * qi], xq_s[4 * qi + 1], xq_s[4 * qi + 2]};
+        const float4 p = park ? s_pts[k] : pts[k];
         const int g = __float_as_int(p.w);
         const float xs[3] = {p.x, p.y, p.z};
         float d[3], s2 = 0.f;
         for (int c = 0; c < dim; ++c) { d[c] = xs[c] - xq[c]; s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c]; }
         const float r = sqrtf(s2);
-        const double e = exp((double)(-P.a * r));
+        const DF e = exp_df(-P.a * r);
         float* col = U + 4 * qi;
         col[k * NCOL] = kf_val(r, P.a, e);
         float k1[3];
@@ -147,7 +237,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     {
         float mu = 0.f;
         if (lane < NCOL)
-            for (int i = warp; i < n; i += E3_WARPS) mu = fmaf(U[i * NCOL + lane], __ldg(alpha + i), mu);
+            for (int i = warp; i < n; i += E3_WARPS) mu = fmaf(U[i * NCOL + lane], park ? s_alpha[i] : __ldg(alpha + i), mu);
         red[warp * 32 + lane] = mu;
         __syncthreads();
         if (warp == 0 && lane < NCOL) {
@@ -162,127 +252,211 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         __syncthreads();
     }
 
-    // ---- block elimination in waves of 32 block rows
-    // Step cursor of this warp: (wave c, column j, quarter q). Active rows at column j: i_r = 32c + warp + 8r
-    // with i_r < nb and i_r > j.
-    struct Cur { int c, j, q; };
+    E3_T(t_elim0)
+    E3_ACC(0, t_begin, t_elim0)   // k* build + mean
+    // ---- block elimination in waves of E3_WAVE block rows, dataflow-synchronised
+    // Warp w owns block rows base + E3_WARPS*r of each wave; accumulator slot s holds the (s+1)-th of them counted
+    // from the END of the wave, so the rows still active at column j are always slots [0, nact). A (sub)visit is
+    // one column j applied to a slot range: normally [0, nact); when this warp owns row j+1 the visit is split —
+    // first the slot of row j+1 alone, then U_{j+1} is published (ready[j+1] = 1), then the remaining slots —
+    // so the next column's operand is available long before the other warps ask for it (lookahead). Consumers
+    // spin on ready[j]; there is no block-wide barrier inside the elimination.
+    struct SV { int valid, c, j, part, split, nact, s_lo, cnt, R, base; };
+    constexpr int W_ = E3_WARPS;
+    // The partial wave comes FIRST (its rows have few columns to eliminate); later waves are full, so the bulk of
+    // the work runs with all E3_R accumulator slots of every warp in use.
     const int nwaves = (nb + E3_WAVE - 1) / E3_WAVE;
-    auto rows_in_wave = [&](int c) { const int lo = E3_WAVE * c + warp; return lo < nb ? min(E3_R, (nb - lo + 7) / 8) : 0; };
-    auto last_j = [&](int c) { return E3_WAVE * c + warp + 8 * (rows_in_wave(c) - 1) - 1; };   // last column with an active row
-    auto cur_valid = [&](const Cur& s) { return s.c < nwaves; };
-    auto normalize = [&](Cur& s) {   // move to the first step at or after s that has work
-        while (s.c < nwaves) {
-            if (rows_in_wave(s.c) > 0 && s.j <= last_j(s.c)) return;
-            ++s.c; s.j = 0; s.q = 0;
-        }
+    const int first_rows = (nb % E3_WAVE) ? (nb % E3_WAVE) : E3_WAVE;
+    auto wstart = [&](int c) { return c == 0 ? 0 : first_rows + (c - 1) * E3_WAVE; };
+    auto wend = [&](int c) { return c == 0 ? min(nb, first_rows) : min(nb, first_rows + c * E3_WAVE); };
+    // Rows of a wave are dealt to the warps in snake order (offset r*W + w for even r, r*W + W-1-w for odd r), so
+    // that every warp carries the same number of tile updates over a full wave (row o has o columns inside it).
+    auto off_of = [&](int r) { return r * W_ + ((r & 1) ? (W_ - 1 - warp) : warp); };
+    auto wave_R = [&](int c) {
+        const int m = wend(c) - wstart(c);
+        int R = 0;
+        for (int r = 0; r < E3_R; ++r) R += (off_of(r) < m) ? 1 : 0;
+        return R;
     };
-    auto advance = [&](Cur s) { if (++s.q == 4) { s.q = 0; ++s.j; } normalize(s); return s; };
-    auto issue = [&](const Cur& s, int st) {
+    auto row_of = [&](int c, int r) { return wstart(c) + off_of(r); };   // r-th row of this warp in wave c, ascending
+    auto make_sv = [&](int c, int j, int part) {
+        SV v;
+        v.valid = 1; v.c = c; v.j = j; v.part = part;
+        v.R = wave_R(c); v.base = wstart(c);
+        int below = 0;
+        for (int r = 0; r < E3_R; ++r) below += (r < v.R && row_of(c, r) <= j) ? 1 : 0;
+        v.nact = v.R - below;
+        v.split = (v.nact > 0 && row_of(c, v.R - v.nact) == j + 1) ? 1 : 0;   // my smallest active row is row j+1
+        if (part == 0) { v.s_lo = v.split ? v.nact - 1 : 0; v.cnt = v.split ? 1 : v.nact; }
+        else { v.s_lo = 0; v.cnt = v.nact - 1; }
+        return v;
+    };
+    auto first_sv = [&](int c, int j) {   // first (sub)visit at or after column j of wave c
+        while (c < nwaves) {
+            const int R = wave_R(c);
+            if (R > 0 && j <= row_of(c, R - 1) - 1) return make_sv(c, j, 0);
+            ++c; j = 0;
+        }
+        SV v; v.valid = 0; v.c = nwaves; v.j = 0; v.part = 0; v.split = 0; v.nact = 0; v.s_lo = 0; v.cnt = 0; v.R = 0; v.base = 0;
+        return v;
+    };
+    auto next_sv = [&](const SV& v) {
+        if (v.part == 0 && v.split && v.nact > 1) return make_sv(v.c, v.j, 1);
+        return first_sv(v.c, v.j + 1);
+    };
+    // tile addresses of a (sub)visit are computed once (by lane 0) and reused for its four quarter steps
+    struct TP { const float* p[E3_R]; const float* solo; };
+    auto tile_ptrs = [&](const SV& v) {
+        TP t;
+        t.solo = nullptr;
+#pragma unroll
+        for (int sl = 0; sl < E3_R; ++sl) {
+            const int i = row_of(v.c, v.R - 1 - sl);
+            t.p[sl] = (sl >= v.s_lo && sl < v.s_lo + v.cnt) ? tiles + (size_t)tile_index(i, v.j, nb) * GPIS_TILE_ELEMS : nullptr;
+            if (sl == v.s_lo) t.solo = t.p[sl];   // static index: keeps the array in registers
+        }
+        return t;
+    };
+#ifdef E3_USE_CPASYNC
+    // cp.async (LDGSTS): every lane moves 2 x 16 B per quarter tile. Measured faster than 1 KB TMA bulk copies for
+    // this access pattern (profiles/r01). The lookahead part of a split visit (one row, R = 1 work) fetches its
+    // whole 4 KB tile at once: its four quarter steps are too short to hide a load each.
+    auto issue = [&](const SV& v, const TP& t, int q, int stage) {
+        if (v.part == 0 && v.split) {
+            const float* src = t.solo + lane * 4;
+            float* dst = stg + stage * E3_STAGE_FLOATS + lane * 4;
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + h * 128)), "l"(src + h * 128) : "memory");
+        } else {
+#pragma unroll
+            for (int sl = 0; sl < E3_R; ++sl)
+                if (t.p[sl]) {
+                    const float* src = t.p[sl] + q * 256 + lane * 4;
+                    float* dst = stg + (stage * E3_R + sl) * 256 + lane * 4;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 128)), "l"(src + 128) : "memory");
+                }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#else
+    auto issue = [&](const SV& v, const TP& t, int q, int stage) {
         if (lane != 0) return;
-        const int base = E3_WAVE * s.c + warp;
-        const int R = rows_in_wave(s.c);
-        int nact = 0;
-        for (int r = 0; r < R; ++r) nact += (base + 8 * r > s.j) ? 1 : 0;
-        mbar_expect_tx(&bars[st], (uint32_t)nact * 1024u);
-        for (int r = 0; r < R; ++r) {
-            const int i = base + 8 * r;
-            if (i > s.j)
-                tma_load_1d(stg + (st * 4 + r) * 256, tiles + (size_t)tile_index(i, s.j, nb) * GPIS_TILE_ELEMS + s.q * 256, 1024u, &bars[st]);
+        if (v.part == 0 && v.split) {
+            mbar_expect_tx(&bars[stage], GPIS_TILE_BYTES);
+            tma_load_1d(stg + stage * E3_STAGE_FLOATS, t.solo, GPIS_TILE_BYTES, &bars[stage]);
+            return;
         }
+        mbar_expect_tx(&bars[stage], (uint32_t)v.cnt * 1024u);
+#pragma unroll
+        for (int sl = 0; sl < E3_R; ++sl)
+            if (t.p[sl]) tma_load_1d(stg + (stage * E3_R + sl) * 256, t.p[sl] + q * 256, 1024u, &bars[stage]);
     };
+#endif
 
     float acc[E3_R][4][CPL];
     uint32_t ph = 0;
     int st = 0;
-    Cur cur{0, 0, 0};
-    normalize(cur);
-    if (cur_valid(cur)) issue(cur, 0);
-
-#define E3_STEP_BEGIN                                                                             \
-    const Cur nxt = advance(cur);                                                                  \
-    if (cur_valid(nxt)) issue(nxt, st ^ 1);                                                        \
-    mbar_wait(&bars[st], (ph >> st) & 1u);                                                         \
-    ph ^= (1u << st);                                                                              \
-    const float* Bq = U + (size_t)(cur.j * 32 + cur.q * 8) * NCOL;                                 \
-    const float* As = stg + st * 1024;
-#define E3_STEP_END                                                                                \
-    __syncwarp();                                                                                  \
-    cur = nxt;                                                                                     \
-    st ^= 1;
+    SV cur = first_sv(0, 0);
+    TP curp = tile_ptrs(cur);
+    if (cur.valid) issue(cur, curp, 0, 0);
+    if (tid == 0) mbar_arrive(&ready[0]);   // row 0 has nothing to eliminate: B_0 is U_0
 
     for (int c = 0; c < nwaves; ++c) {
-        const int wbase = E3_WAVE * c;
-        const int base = wbase + warp;
-        const int R = rows_in_wave(c);
-        // accumulators <- right-hand sides of this warp's rows
+        const int R = wave_R(c);
+        if (R == 0) continue;
+        // accumulators <- right-hand sides of this warp's rows (slot s = its (R-1-s)-th row, ascending)
 #pragma unroll
         for (int r = 0; r < E3_R; ++r) {
             if (r < R) {
-                const float* Ui = U + (size_t)(base + 8 * r) * 32 * NCOL;
+                const float* Ui = U + (size_t)row_of(c, R - 1 - r) * 32 * NCOL;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int v = 0; v < CPL / 4; ++v) {
-                        const float4 t = *reinterpret_cast<const float4*>(Ui + (4 * rg + i) * NCOL + CPL * cg + 4 * v);
-                        acc[r][i][4 * v] = t.x; acc[r][i][4 * v + 1] = t.y; acc[r][i][4 * v + 2] = t.z; acc[r][i][4 * v + 3] = t.w;
-                    }
+                    ld_cols<CPL>(Ui + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
             }
         }
-        // phase 1: columns of earlier waves, all rows active, no block-level synchronisation
-        if (R > 0) {
-            for (int j = 0; j < wbase; ++j)
-                for (int q = 0; q < 4; ++q) {
-                    E3_STEP_BEGIN
-                    qmma_dispatch<CPL, NCOL>(0, R, acc, As, Bq, rg, cg);
-                    E3_STEP_END
+        while (cur.valid && cur.c == c) {
+            const SV nxt = next_sv(cur);
+            const TP nxtp = tile_ptrs(nxt);
+            // operand U_j must be final (published by the owner of row j)
+            E3_T(t_r0)
+            if (cur.part == 0) mbar_wait(&ready[cur.j], 0u);   // hardware-suspended wait, acquire semantics
+            E3_T(t_r1)
+            E3_ACC(1, t_r0, t_r1)   // waiting for the operand U_j
+            const float* Uj = U + (size_t)cur.j * 32 * NCOL;
+            const bool solo = (cur.part == 0 && cur.split);   // lookahead part: its whole tile was staged at once
+            for (int q = 0; q < 4; ++q) {
+                E3_T(t_s0)
+                // what to prefetch during this step: the next quarter of this visit, or the first step of the next
+                // one; a solo visit owns its stage for all four quarters and prefetches only once
+                const bool do_wait = !solo || q == 0;
+                if (do_wait) {
+                    bool issued = true;
+                    if (!solo && q < 3) issue(cur, curp, q + 1, st ^ 1);
+                    else if (nxt.valid) issue(nxt, nxtp, 0, st ^ 1);
+                    else issued = false;
+#ifdef E3_USE_CPASYNC
+                    if (issued) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+#else
+                    (void)issued;
+                    mbar_wait(&bars[st], (ph >> st) & 1u);
+                    ph ^= (1u << st);
+#endif
                 }
-        }
-        // phase 2: the wave's own columns; the owner of row j publishes U_j, then later rows consume it
-        const int tcount = min(E3_WAVE, nb - wbase);
-        for (int t = 0; t < tcount; ++t) {
-            const int j = wbase + t;
-            if ((t & 7) == warp) {
-                const int ro = t >> 3;   // which of this warp's rows is row j
-                float* Uj = U + (size_t)j * 32 * NCOL;
+                E3_T(t_s1)
+                E3_ACC(2, t_s0, t_s1)   // issue + waiting for the staged tiles
+                const float* Bq = Uj + q * 8 * NCOL;
+                // solo: quarter q of the tile sits at stage + q*256 and the micro-kernel adds slot*256 itself
+                const float* As = stg + st * E3_STAGE_FLOATS + (solo ? (q - cur.s_lo) * 256 : 0);
+                if (cur.s_lo == 0 && !solo) qmma_dispatch<CPL, NCOL>(cur.cnt, acc, As, Bq, rg, cg);
+                else qmma_dispatch_one<CPL, NCOL>(cur.s_lo, acc, As, Bq, rg, cg);
+                __syncwarp();
+                if (!solo || q == 3) st ^= 1;
+                E3_T(t_s2)
+                E3_ACC(3, t_s1, t_s2)   // FMA work
+#ifdef E3_TIMING
+                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 16 + 8] += cur.cnt; g_e3_timing[warp * 16 + 9] += 1; }
+#endif
+            }
+            if (cur.part == 0 && cur.split) {
+                // row j+1 (slot s_lo) is final: publish it
+                float* Un = U + (size_t)(cur.j + 1) * 32 * NCOL;
 #pragma unroll
                 for (int r = 0; r < E3_R; ++r) {
-                    if (r == ro) {
+                    if (r == cur.s_lo) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int v = 0; v < CPL / 4; ++v)
-                                *reinterpret_cast<float4*>(Uj + (4 * rg + i) * NCOL + CPL * cg + 4 * v) =
-                                    make_float4(acc[r][i][4 * v], acc[r][i][4 * v + 1], acc[r][i][4 * v + 2], acc[r][i][4 * v + 3]);
+                            st_cols<CPL>(Un + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[cur.j + 1]);   // release: the stores above are visible to waiters
             }
-            __syncthreads();   // U_j is final and visible
-            // rows of this warp below j: r >= r0
-            int r0 = 0;
-            while (r0 < R && base + 8 * r0 <= j) ++r0;
-            const int nact = R - r0;
-            if (nact > 0) {
-                for (int q = 0; q < 4; ++q) {
-                    E3_STEP_BEGIN
-                    qmma_dispatch<CPL, NCOL>(r0, R, acc, As, Bq, rg, cg);   // TMA filled slots r0..R-1
-                    E3_STEP_END
-                }
-            }
+            cur = nxt;
+            curp = nxtp;
         }
     }
-#undef E3_STEP_BEGIN
-#undef E3_STEP_END
+    E3_T(t_elim1)
     __syncthreads();
+    E3_T(t_elim2)
+    E3_ACC(4, t_elim0, t_elim1)   // whole elimination of this warp
+    E3_ACC(5, t_elim1, t_elim2)   // waiting at the closing barrier
+
 
     // ---- V_j = Dinv(j) U_j and the column sums of V^2 (OnGPIS.cpp:200-201); warp w takes j = w, w+8, ...
     float ss[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) ss[c] = 0.f;
     {
+        // one full 4 KB Dinv tile per step (a stage holds exactly one tile), double buffered
+        static_assert(E3_R == 4, "a stage must hold one full tile");
         auto issue_d = [&](int j, int s2) {
             if (lane == 0) {
                 mbar_expect_tx(&bars[s2], GPIS_TILE_BYTES);
-                tma_load_1d(stg + s2 * 1024, dinv + (size_t)j * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s2]);
+                tma_load_1d(stg + s2 * E3_STAGE_FLOATS, dinv + (size_t)j * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s2]);
             }
         };
         if (warp < nb) issue_d(warp, st);
@@ -296,9 +470,8 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
 #pragma unroll
                 for (int jj = 0; jj < CPL; ++jj) v[0][i][jj] = 0.f;
             const float* Uj = U + (size_t)j * 32 * NCOL;
-            // a full tile is four consecutive quarter tiles: slot q of this stage
 #pragma unroll
-            for (int q = 0; q < 4; ++q) qmma_sub<0, 1, CPL, NCOL>(v, stg + st * 1024 + q * 1024 / 4, Uj + q * 8 * NCOL, rg, cg);
+            for (int q = 0; q < 4; ++q) qmma_sub<1, CPL, NCOL>(v, stg + st * E3_STAGE_FLOATS + q * 256, Uj + q * 8 * NCOL, rg, cg);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -330,14 +503,19 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + w + c] = (float)(prior - (double)s);
         }
     }
+#ifdef E3_TIMING
+    { const long long t_end = clock64(); if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 16 + 6] += t_end - t_elim2; g_e3_timing[warp * 16 + 7] = nb; } }
+#endif
 }
 
 // ------------------------------------------------------------------ host side
 #define E3_NB_A 40   // 8 queries per CTA: U = nb * 4 KB  (n <= 1280)
+#define E3_NB_M 53   // 6 queries per CTA: U = nb * 3 KB  (n <= 1696)
 #define E3_NB_B 80   // 4 queries per CTA: U = nb * 2 KB  (n <= 2560); larger leaves go to k_eval_v1
 
 static inline int query_eval_init(std::string& err) {
     cudaError_t e = cudaFuncSetAttribute(k_eval_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_v3<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(k_eval_*): ") + cudaGetErrorString(e); return -2; }
@@ -356,7 +534,7 @@ static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable&
         if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return -2; } \
     } while (0)
     const int64_t max_items = npairs / 4 + nslots + 8;
-    const int64_t need = (int64_t)nslots * 4 + 64 + (int64_t)npairs * 4 + max_items * 8 + 64;
+    const int64_t need = (int64_t)nslots * 4 + 64 + (int64_t)npairs * 4 + max_items * 12 + 64;
     if (*sort_cap < need) {
         if (*d_sort) CK2(cudaFree(*d_sort));
         *d_sort = nullptr; *sort_cap = 0;
@@ -373,6 +551,7 @@ static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable&
     p += (4 - (((uintptr_t)p >> 2) & 3)) & 3;   // 16-byte align for int4
     S.items = reinterpret_cast<int4*>(p); p += max_items * 4;
     S.itemsB = reinterpret_cast<int4*>(p); p += max_items * 4;
+    S.itemsM = reinterpret_cast<int4*>(p); p += max_items * 4;
     S.sorted = reinterpret_cast<int2*>(p); p += (int64_t)npairs * 2;
     S.pairsC = reinterpret_cast<int2*>(p);
     CK2(cudaMemsetAsync(S.totals, 0, sizeof(int32_t) * 16, st));
@@ -402,14 +581,19 @@ static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable&
         }
         return 0;
     }
-    k_make_items_classed<<<(nslots + 255) / 256, 256, 0, st>>>(S, T, nslots, E3_NB_A, E3_NB_B);
+    k_make_items_classed<<<(nslots + 255) / 256, 256, 0, st>>>(S, T, nslots, E3_NB_A, E3_NB_M, E3_NB_B);
     *launches += 1;
-    int32_t tot[4] = {0, 0, 0, 0};
-    CK2(cudaMemcpyAsync(tot, S.totals, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
+    int32_t tot[5] = {0, 0, 0, 0, 0};
+    CK2(cudaMemcpyAsync(tot, S.totals, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
     CK2(cudaStreamSynchronize(st));
     if (tot[1] > 0) {
         const int nbm = max_nb < E3_NB_A ? max_nb : E3_NB_A;
         k_eval_v3<8><<<tot[1], E3_THREADS, Eval3Smem::total(nbm, 32), st>>>(d_x, T, P, W, S, S.items);
+        *launches += 1;
+    }
+    if (tot[4] > 0) {
+        const int nbm = max_nb < E3_NB_M ? max_nb : E3_NB_M;
+        k_eval_v3<6><<<tot[4], E3_THREADS, Eval3Smem::total(nbm, 24), st>>>(d_x, T, P, W, S, S.itemsM);
         *launches += 1;
     }
     if (tot[2] > 0) {

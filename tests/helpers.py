@@ -113,7 +113,7 @@ G_FLOOR = 0.1
 V_FLOOR = 1e-3
 
 
-def check_rows(got, want32, want64, dim, tol_f=1e-4, tol_v=1e-3, label=""):
+def check_rows(got, want32, want64, dim, tol_f=1e-4, tol_v=1e-3, label="", max_unpinned=0.05):
     """north_star tolerances: relative 1e-4 on f and grad f, 1e-3 on the variances, "in the reference's
     scalar precision" (fp32). Two fp32 evaluations of the same formulas with different summation orders
     (Eigen vs any other LA) agree to that level only where the problem is conditioned well enough for
@@ -140,5 +140,5 @@ def check_rows(got, want32, want64, dim, tol_f=1e-4, tol_v=1e-3, label=""):
         assert worst_a < tols[k], f"{label} {names[k]}: {worst_a:.3e} >= {tols[k]:.0e} on a row the fp32 oracle pins ({rep})"
         assert okb.all(), (f"{label} {names[k]}: {int((~okb).sum())} rows are further from fp64 than 4x the fp32 oracle "
                            f"(worst {float(e_g64[k][~stable][~okb].max()):.3e})")
-        assert (~stable).sum() <= max(5, 0.05 * n), f"{label} {names[k]}: {int((~stable).sum())}/{n} rows unpinned by fp32"
+        assert (~stable).sum() <= max(5, max_unpinned * n), f"{label} {names[k]}: {int((~stable).sum())}/{n} rows unpinned by fp32"
     return rep
