@@ -23,6 +23,10 @@
 
 namespace gpis {
 
+// Tile staging: cp.async by default; -DE3_USE_TMA selects 1 KB TMA bulk copies (measured 12 % slower, profiles/r01)
+#if !defined(E3_USE_TMA) && !defined(E3_USE_CPASYNC)
+#define E3_USE_CPASYNC 1
+#endif
 #ifndef E3_WARPS
 #define E3_WARPS 8
 #endif
@@ -440,28 +444,42 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         }
     }
     E3_T(t_elim1)
-    __syncthreads();
     E3_T(t_elim2)
     E3_ACC(4, t_elim0, t_elim1)   // whole elimination of this warp
-    E3_ACC(5, t_elim1, t_elim2)   // waiting at the closing barrier
 
-
-    // ---- V_j = Dinv(j) U_j and the column sums of V^2 (OnGPIS.cpp:200-201); warp w takes j = w, w+8, ...
+    // ---- V_j = Dinv(j) U_j and the column sums of V^2 (OnGPIS.cpp:200-201) for the rows THIS warp owns: they are
+    // final and were written to shared memory by this warp itself, so no block-wide barrier is needed and a warp
+    // that finishes its elimination early starts here while the others are still eliminating.
     float ss[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) ss[c] = 0.f;
     {
-        // one full 4 KB Dinv tile per step (a stage holds exactly one tile), double buffered
         static_assert(E3_R == 4, "a stage must hold one full tile");
+        // owned rows in order: wave c, r = 0 .. wave_R(c)-1
+        auto next_owned = [&](int& c, int& r) {   // advance (c, r) to the next owned row; returns -1 at the end
+            while (c < nwaves) {
+                if (r < wave_R(c)) return row_of(c, r);
+                ++c; r = 0;
+            }
+            return -1;
+        };
         auto issue_d = [&](int j, int s2) {
             if (lane == 0) {
                 mbar_expect_tx(&bars[s2], GPIS_TILE_BYTES);
                 tma_load_1d(stg + s2 * E3_STAGE_FLOATS, dinv + (size_t)j * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s2]);
             }
         };
-        if (warp < nb) issue_d(warp, st);
-        for (int j = warp; j < nb; j += E3_WARPS) {
-            if (j + E3_WARPS < nb) issue_d(j + E3_WARPS, st ^ 1);
+#ifdef E3_USE_CPASYNC
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+#endif
+        int vc = 0, vr = 0;
+        int j = next_owned(vc, vr);
+        if (j >= 0) issue_d(j, st);
+        while (j >= 0) {
+            ++vr;
+            const int jn = next_owned(vc, vr);
+            if (jn >= 0) issue_d(jn, st ^ 1);
             mbar_wait(&bars[st], (ph >> st) & 1u);
             ph ^= (1u << st);
             float v[E3_R][4][CPL];
@@ -478,6 +496,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 for (int jj = 0; jj < CPL; ++jj) ss[jj] = fmaf(v[0][i][jj], v[0][i][jj], ss[jj]);   // (-V)^2 = V^2
             __syncwarp();
             st ^= 1;
+            j = jn;
         }
     }
 #pragma unroll
