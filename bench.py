@@ -313,7 +313,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "kernel": "k_eval_v2 (+ bucketing)", "peak_source": peak_src,
+                         "traffic": None, "kernel": "k_eval_v3<8>/<6>/<4> (+ bucketing)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": comp_bytes,
                          "note": "HBM term uses compulsory bytes (44 B/query + each touched leaf record once per pass); "
                                  "the binding roofline of this kernel is FP32 FMA, see roofline_fp32"},
@@ -322,7 +322,9 @@ def main():
                               "flops_per_step": sq["last_query_flops"],
                               "peak_source": f"{props.multi_processor_count} SMs x 128 lanes x 2 x {sm_clock/1e6:.0f} MHz (median SM clock under load)"},
             "query_breakdown": {"evaluations_per_step": evals_total, "eval_kernel_ms": float(np.mean(eval_ms_steps)),
-                                "all_kernels_ms": my_ms, "wall_ms_per_step": wall_all},
+                                "all_kernels_ms": my_ms, "wall_ms_per_step": wall_all,
+                                "eval_ctas_8_6_4_1": sq["last_query_items"],
+                                "batch_fill": (sq["last_query_evals"] / max(1, sum(c * q for c, q in zip(sq["last_query_items"], (8, 6, 4, 1)))))},
             "map": {"leaves": sq["leaves"], "leaves_trained": sq["leaves_trained"],
                     "arena_gb": sq["arena_bytes_used"] / 1e9, "build_s": t_build,
                     "update_ms_per_frame_median": float(np.median(update_ms)) if update_ms else None,

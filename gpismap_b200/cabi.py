@@ -39,7 +39,7 @@ class Stats(C.Structure):
         ("last_query_n", C.c_int64), ("last_query_evals", C.c_int64),
         ("last_query_flops", C.c_double), ("last_query_bytes_gather", C.c_double),
         ("last_query_bytes_compulsory", C.c_double), ("last_query_ms", C.c_float), ("last_query_eval_ms", C.c_float),
-        ("kernel_launches", C.c_int64),
+        ("kernel_launches", C.c_int64), ("last_query_items", C.c_int64 * 4),
     ]
 
 
@@ -232,7 +232,7 @@ class Ctx:
     def stats(self):
         s = Stats()
         self._ck(lib().gpis_get_stats(self.h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in Stats._fields_}
+        return {k: (list(getattr(s, k)) if k == "last_query_items" else getattr(s, k)) for k, _ in Stats._fields_}
 
     def set_eval_version(self, v):
         self._ck(lib().gpis_set_eval_version(self.h, v))

@@ -205,4 +205,31 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// Packed fp32x2 FMA (sm_100 FFMA2): two IEEE fma.rn results per issue slot, bit-identical to two fmaf().
+// (c0, c1) -= (a0, a1) * b   and   (c0, c1) += (a0, a1) * b. ptxas folds the pack/unpack moves when the
+// pairs sit in aligned adjacent registers (they do when they come from 8/16-byte loads) and the negation
+// into the instruction's broadcast-operand modifier.
+#ifndef GPIS_NO_FFMA2
+__device__ __forceinline__ void fma2_sub(float& c0, float& c1, float a0, float a1, float b) {
+    uint64_t aa, bb, cc;
+    const float nb = -b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(nb));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(cc));
+}
+__device__ __forceinline__ void fma2_add(float& c0, float& c1, float a0, float a1, float b) {
+    uint64_t aa, bb, cc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(cc));
+}
+#else
+__device__ __forceinline__ void fma2_sub(float& c0, float& c1, float a0, float a1, float b) { c0 = fmaf(-a0, b, c0); c1 = fmaf(-a1, b, c1); }
+__device__ __forceinline__ void fma2_add(float& c0, float& c1, float a0, float a1, float b) { c0 = fmaf(a0, b, c0); c1 = fmaf(a1, b, c1); }
+#endif
+
 }  // namespace gpis

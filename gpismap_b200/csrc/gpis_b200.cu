@@ -678,6 +678,7 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
     QueryWork W = ctx->W;
     double flops = 0, bytes_g = 0;
     int64_t evals = 0;
+    int64_t items[4] = {0, 0, 0, 0};
     float ms_total = 0.f, ms_eval = 0.f;
     if (!ctx->d_acc) CK(cudaMalloc(&ctx->d_acc, sizeof(double) * 4));
     CK(cudaMemsetAsync(ctx->d_acc, 0, sizeof(double) * 4, ctx->stream));
@@ -705,7 +706,7 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
                 {
                     int rc = query_eval(ctx->stream, xq, ctx->T, ctx->qp, W, npairs, ctx->slot_count, ctx->max_nb,
                                         &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err, ctx->d_acc,
-                                        ctx->eval_version);
+                                        ctx->eval_version, items);
                     if (rc) return rc;
                 }
                 CK(cudaGetLastError());
@@ -731,6 +732,7 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
     ctx->st.last_query_evals = evals;
     ctx->st.last_query_ms = ms_total;
     ctx->st.last_query_eval_ms = ms_eval;
+    for (int i = 0; i < 4; ++i) ctx->st.last_query_items[i] = items[i];
     double acc[4] = {0, 0, 0, 0};
     CK(cudaMemcpy(acc, ctx->d_acc, sizeof(double) * 3, cudaMemcpyDeviceToHost));
     ctx->st.last_query_flops = acc[0];
@@ -1006,9 +1008,9 @@ int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out) {
 }
 
 #ifdef E3_TIMING
-int gpis_debug_timing(long long* out) {   // 64 warps x 16 counters of the instrumented CTA, then reset
-    cudaMemcpyFromSymbol(out, g_e3_timing, sizeof(long long) * 64 * 16);
-    static long long zeros[64 * 16];
+int gpis_debug_timing(long long* out) {   // 64 warps x 32 counters of the instrumented CTA, then reset
+    cudaMemcpyFromSymbol(out, g_e3_timing, sizeof(long long) * 64 * 32);
+    static long long zeros[64 * 32];
     cudaMemcpyToSymbol(g_e3_timing, zeros, sizeof(zeros));
     return 0;
 }

@@ -77,22 +77,33 @@ __device__ __forceinline__ void st_cols(float* __restrict__ p, const float (&v)[
 // acc[s][i][j] -= sum_{k<8} A_s[k][4rg+i] * B[k][CPL*cg+j] for accumulator slots s < R;  A_s: quarter tile
 // [8][32] at As + s*256, B: [8][NCOL] rows of U. Slots are ordered from the warp's LAST block row of the
 // wave upwards, so the rows still active at a column are always a prefix and R is the only variant.
-// k is unrolled by 2 only: the four variants together must stay inside the instruction cache.
 template <int R, int CPL, int NCOL>
 __device__ __forceinline__ void qmma_sub(float (&acc)[E3_R][4][CPL], const float* __restrict__ As,
                                          const float* __restrict__ Bq, int rg, int cg) {
-#pragma unroll 2
+    // software pipelined over k: the operands of step k+1 are loaded before the FMAs of step k are issued, so
+    // the shared-memory latency is covered by this warp's own FMAs (two register operand buffers)
+    const float* Ap = As + 4 * rg;
+    const float* Bp = Bq + CPL * cg;
+    float bv[2][CPL];
+    float4 av[2][R];
+    ld_cols<CPL>(Bp, bv[0]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) av[0][r] = *reinterpret_cast<const float4*>(Ap + r * 256);
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
-        float bv[CPL];
-        ld_cols<CPL>(Bq + k * NCOL + CPL * cg, bv);
+        const int cu = k & 1, nx = cu ^ 1;
+        if (k + 1 < 8) {
+            ld_cols<CPL>(Bp + (k + 1) * NCOL, bv[nx]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) av[nx][r] = *reinterpret_cast<const float4*>(Ap + r * 256 + (k + 1) * 32);
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const float4 a = *reinterpret_cast<const float4*>(As + r * 256 + k * 32 + 4 * rg);
-            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float a4[4] = {av[cu][r].x, av[cu][r].y, av[cu][r].z, av[cu][r].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) acc[r][i][j] = fmaf(-av[i], bv[j], acc[r][i][j]);
+                for (int j = 0; j < CPL; j += 2) fma2_sub(acc[r][i][j], acc[r][i][j + 1], bv[cu][j], bv[cu][j + 1], a4[i]);
         }
     }
 }
@@ -100,16 +111,24 @@ __device__ __forceinline__ void qmma_sub(float (&acc)[E3_R][4][CPL], const float
 template <int S, int CPL, int NCOL>
 __device__ __forceinline__ void qmma_one(float (&acc)[E3_R][4][CPL], const float* __restrict__ As,
                                          const float* __restrict__ Bq, int rg, int cg) {
-#pragma unroll 2
+    const float* Ap = As + S * 256 + 4 * rg;
+    const float* Bp = Bq + CPL * cg;
+    float bv[2][CPL];
+    float4 av[2];
+    ld_cols<CPL>(Bp, bv[0]);
+    av[0] = *reinterpret_cast<const float4*>(Ap);
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
-        float bv[CPL];
-        ld_cols<CPL>(Bq + k * NCOL + CPL * cg, bv);
-        const float4 a = *reinterpret_cast<const float4*>(As + S * 256 + k * 32 + 4 * rg);
-        const float av[4] = {a.x, a.y, a.z, a.w};
+        const int cu = k & 1, nx = cu ^ 1;
+        if (k + 1 < 8) {
+            ld_cols<CPL>(Bp + (k + 1) * NCOL, bv[nx]);
+            av[nx] = *reinterpret_cast<const float4*>(Ap + (k + 1) * 32);
+        }
+        const float a4[4] = {av[cu].x, av[cu].y, av[cu].z, av[cu].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) acc[S][i][j] = fmaf(-av[i], bv[j], acc[S][i][j]);
+            for (int j = 0; j < CPL; j += 2) fma2_sub(acc[S][i][j], acc[S][i][j + 1], bv[cu][j], bv[cu][j + 1], a4[i]);
     }
 }
 template <int CPL, int NCOL>
@@ -145,9 +164,9 @@ __device__ __forceinline__ void qmma_dispatch(int nact, float (&acc)[E3_R][4][CP
 }
 
 #ifdef E3_TIMING
-__device__ long long g_e3_timing[64 * 16];   // [warp][phase] accumulated clock64 ticks of blockIdx.x == E3_TIMING
+__device__ long long g_e3_timing[64 * 32];   // [warp][phase] accumulated clock64 ticks of blockIdx.x == E3_TIMING
 #define E3_T(var) const long long var = clock64();
-#define E3_ACC(slot, t0, t1) if (blockIdx.x == E3_TIMING && lane == 0) g_e3_timing[warp * 16 + (slot)] += (t1) - (t0);
+#define E3_ACC(slot, t0, t1) if (blockIdx.x == E3_TIMING && lane == 0) g_e3_timing[warp * 32 + (slot)] += (t1) - (t0);
 #else
 #define E3_T(var)
 #define E3_ACC(slot, t0, t1)
@@ -422,7 +441,8 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 E3_T(t_s2)
                 E3_ACC(3, t_s1, t_s2)   // FMA work
 #ifdef E3_TIMING
-                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 16 + 8] += cur.cnt; g_e3_timing[warp * 16 + 9] += 1; }
+                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 32 + 8] += cur.cnt; g_e3_timing[warp * 32 + 9] += 1;
+                    g_e3_timing[warp * 32 + 16 + cur.cnt] += t_s2 - t_s1; g_e3_timing[warp * 32 + 24 + cur.cnt] += 1; }
 #endif
             }
             if (cur.part == 0 && cur.split) {
@@ -523,7 +543,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         }
     }
 #ifdef E3_TIMING
-    { const long long t_end = clock64(); if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 16 + 6] += t_end - t_elim2; g_e3_timing[warp * 16 + 7] = nb; } }
+    { const long long t_end = clock64(); if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 32 + 6] += t_end - t_elim2; g_e3_timing[warp * 32 + 7] = nb; } }
 #endif
 }
 
@@ -546,7 +566,8 @@ static inline int query_eval_init(std::string& err) {
 // 3 = production kernel.
 static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable& T, const QueryParams& P,
                              const QueryWork& W, int npairs, int nslots, int max_nb, int32_t** d_sort,
-                             int64_t* sort_cap, int64_t* launches, std::string& err, double* d_acc, int version) {
+                             int64_t* sort_cap, int64_t* launches, std::string& err, double* d_acc, int version,
+                             int64_t* items_out = nullptr) {
 #define CK2(call)                                                                 \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -605,6 +626,7 @@ static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable&
     int32_t tot[5] = {0, 0, 0, 0, 0};
     CK2(cudaMemcpyAsync(tot, S.totals, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
     CK2(cudaStreamSynchronize(st));
+    if (items_out) { items_out[0] += tot[1]; items_out[1] += tot[4]; items_out[2] += tot[2]; items_out[3] += tot[3]; }
     if (tot[1] > 0) {
         const int nbm = max_nb < E3_NB_A ? max_nb : E3_NB_A;
         k_eval_v3<8><<<tot[1], E3_THREADS, Eval3Smem::total(nbm, 32), st>>>(d_x, T, P, W, S, S.items);

@@ -176,6 +176,8 @@ typedef struct gpis_stats {
     float last_query_ms;       /* CUDA-event time of the query kernels (no H2D/D2H) */
     float last_query_eval_ms;  /* ... of which the leaf-evaluation (solve) kernels */
     int64_t kernel_launches;   /* kernels of this library launched since gpis_create */
+    /* last gpis_query*: evaluation CTAs launched with 8, 6, 4 and 1 queries per CTA (batch fill = evals / capacity) */
+    int64_t last_query_items[4];
 } gpis_stats;
 int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out);
 
