@@ -146,6 +146,7 @@ struct gpis_ctx {
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
+    EvalProg prog{nullptr, nullptr};   // elimination programs of k_eval_v3 (query_v3.cuh)
     double* d_acc = nullptr;
     // obs gp
     ObsTile* obs_tiles = nullptr; int obs_tile_cap = 0;
@@ -354,6 +355,7 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
     CK(cudaFuncSetAttribute(k_leaf_train, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_eval_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     rc = query_eval_init(ctx->err);
+    if (rc == 0) rc = e3_upload_programs(const_cast<int4**>(&ctx->prog.recs), const_cast<int32_t**>(&ctx->prog.off), ctx->err);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return GPIS_OK;
@@ -369,6 +371,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_scratch2);
     cudaFree(ctx->W.cand); cudaFree(ctx->W.tie); cudaFree(ctx->W.evalout); cudaFree(ctx->W.pairs); cudaFree(ctx->W.counters);
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
+    cudaFree(const_cast<int4*>(ctx->prog.recs)); cudaFree(const_cast<int32_t*>(ctx->prog.off));
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
     cudaFree(ctx->d_export); cudaFree(ctx->d_acc);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -706,7 +709,7 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
                 {
                     int rc = query_eval(ctx->stream, xq, ctx->T, ctx->qp, W, npairs, ctx->slot_count, ctx->max_nb,
                                         &ctx->d_sort, &ctx->sort_cap, &ctx->st.kernel_launches, ctx->err, ctx->d_acc,
-                                        ctx->eval_version, items);
+                                        ctx->eval_version, ctx->prog, items);
                     if (rc) return rc;
                 }
                 CK(cudaGetLastError());

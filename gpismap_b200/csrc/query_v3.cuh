@@ -15,7 +15,9 @@
 // step ahead and running across column and wave boundaries (G is read-only). A row's tile of U is written
 // to shared memory exactly once, when it becomes final. One __syncthreads per block column.
 #pragma once
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "query.cuh"
@@ -163,6 +165,92 @@ __device__ __forceinline__ void qmma_dispatch(int nact, float (&acc)[E3_R][4][CP
     }
 }
 
+
+// ------------------------------------------------------------------ elimination programs
+// The order in which a warp visits (block row, block column) pairs depends only on (nb, warp). It is generated
+// once on the host (same rules the kernel used to evaluate inline: waves of E3_WAVE block rows, the partial
+// wave first, snake dealing, split visits for the lookahead) and read by the kernel as a table: two int4 per
+// record, uniform loads, no per-visit index arithmetic on the device.
+//   header  : {nwaves, nvisits, 0, 0}, {0,0,0,0}
+//   wave c  : {R, 0, 0, 0}, {row of slot 0, 1, 2, 3}                 (slot s = the warp's (R-1-s)-th row, ascending)
+//   visit v : {j, flags, solo tile, nact}, {tile of slot 0, 1, 2, 3}   (tile = index into the leaf's tile array, -1 = idle)
+//             flags: bits 0-2 s_lo, 3-5 cnt, 6 part, 7 split, 8 valid, 16-23 wave
+struct EvalProg {
+    const int4* recs;       // all programs
+    const int32_t* off;     // [E3_PROG_MAXNB + 1][E3_WARPS] record offset of (nb, warp)
+};
+#define E3_PROG_MAXNB 80
+
+static inline void e3_build_program(int nb, int warp, std::vector<int4>& out) {
+    const int W_ = E3_WARPS;
+    const int nwaves = (nb + E3_WAVE - 1) / E3_WAVE;
+    const int first_rows = (nb % E3_WAVE) ? (nb % E3_WAVE) : E3_WAVE;
+    auto wstart = [&](int c) { return c == 0 ? 0 : first_rows + (c - 1) * E3_WAVE; };
+    auto wend = [&](int c) { return c == 0 ? std::min(nb, first_rows) : std::min(nb, first_rows + c * E3_WAVE); };
+    auto off_of = [&](int r) { return r * W_ + ((r & 1) ? (W_ - 1 - warp) : warp); };
+    auto wave_R = [&](int c) {
+        const int m = wend(c) - wstart(c);
+        int R = 0;
+        for (int r = 0; r < E3_R; ++r) R += (off_of(r) < m) ? 1 : 0;
+        return R;
+    };
+    auto row_of = [&](int c, int r) { return wstart(c) + off_of(r); };
+    const size_t head = out.size();
+    out.push_back(make_int4(nwaves, 0, 0, 0));
+    out.push_back(make_int4(0, 0, 0, 0));
+    for (int c = 0; c < nwaves; ++c) {
+        const int R = wave_R(c);
+        int rows[4] = {-1, -1, -1, -1};
+        for (int sl = 0; sl < R; ++sl) rows[sl] = row_of(c, R - 1 - sl);
+        out.push_back(make_int4(R, 0, 0, 0));
+        out.push_back(make_int4(rows[0], rows[1], rows[2], rows[3]));
+    }
+    int nvis = 0;
+    for (int c = 0; c < nwaves; ++c) {
+        const int R = wave_R(c);
+        if (R == 0) continue;
+        const int last = row_of(c, R - 1);
+        for (int j = 0; j < last; ++j) {
+            int below = 0;
+            for (int r = 0; r < R; ++r) below += (row_of(c, r) <= j) ? 1 : 0;
+            const int nact = R - below;
+            if (nact <= 0) break;
+            const bool split = row_of(c, R - nact) == j + 1;
+            for (int part = 0; part < 2; ++part) {
+                int s_lo, cnt;
+                if (part == 0) { s_lo = split ? nact - 1 : 0; cnt = split ? 1 : nact; }
+                else { if (!(split && nact > 1)) break; s_lo = 0; cnt = nact - 1; }
+                int t[4] = {-1, -1, -1, -1};
+                for (int sl = 0; sl < E3_R; ++sl)
+                    if (sl >= s_lo && sl < s_lo + cnt) t[sl] = tile_index(row_of(c, R - 1 - sl), j, nb);
+                const int flags = s_lo | (cnt << 3) | (part << 6) | ((split ? 1 : 0) << 7) | (1 << 8) | (c << 16);
+                out.push_back(make_int4(j, flags, t[s_lo], nact));
+                out.push_back(make_int4(t[0], t[1], t[2], t[3]));
+                ++nvis;
+            }
+        }
+    }
+    out.push_back(make_int4(0, 0, -1, 0));   // terminator: valid bit clear
+    out.push_back(make_int4(-1, -1, -1, -1));
+    out[head].y = nvis;
+}
+// all (nb, warp) programs -> device
+static inline int e3_upload_programs(int4** d_recs, int32_t** d_off, std::string& err) {
+    std::vector<int4> recs;
+    std::vector<int32_t> off((E3_PROG_MAXNB + 1) * E3_WARPS, 0);
+    for (int nb = 1; nb <= E3_PROG_MAXNB; ++nb)
+        for (int w = 0; w < E3_WARPS; ++w) {
+            off[nb * E3_WARPS + w] = (int32_t)recs.size();
+            e3_build_program(nb, w, recs);
+        }
+    cudaError_t e = cudaMalloc(d_recs, recs.size() * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMalloc(d_off, off.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(*d_recs, recs.data(), recs.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(*d_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { err = std::string("elimination programs: ") + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
 #ifdef E3_TIMING
 __device__ long long g_e3_timing[64 * 32];   // [warp][phase] accumulated clock64 ticks of blockIdx.x == E3_TIMING
 #define E3_T(var) const long long var = clock64();
@@ -174,7 +262,8 @@ __device__ long long g_e3_timing[64 * 32];   // [warp][phase] accumulated clock6
 
 template <int QBT>
 __global__ void __launch_bounds__(E3_THREADS, 1)
-k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, SortBufs S, const int4* __restrict__ items) {
+k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, SortBufs S, const int4* __restrict__ items,
+          EvalProg G) {
     constexpr int NCOL = 4 * QBT;      // right-hand sides per CTA
     constexpr int CPL = NCOL / 4;      // columns per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -284,124 +373,89 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     // first the slot of row j+1 alone, then U_{j+1} is published (ready[j+1] = 1), then the remaining slots —
     // so the next column's operand is available long before the other warps ask for it (lookahead). Consumers
     // spin on ready[j]; there is no block-wide barrier inside the elimination.
-    struct SV { int valid, c, j, part, split, nact, s_lo, cnt, R, base; };
-    constexpr int W_ = E3_WARPS;
-    // The partial wave comes FIRST (its rows have few columns to eliminate); later waves are full, so the bulk of
-    // the work runs with all E3_R accumulator slots of every warp in use.
-    const int nwaves = (nb + E3_WAVE - 1) / E3_WAVE;
-    const int first_rows = (nb % E3_WAVE) ? (nb % E3_WAVE) : E3_WAVE;
-    auto wstart = [&](int c) { return c == 0 ? 0 : first_rows + (c - 1) * E3_WAVE; };
-    auto wend = [&](int c) { return c == 0 ? min(nb, first_rows) : min(nb, first_rows + c * E3_WAVE); };
-    // Rows of a wave are dealt to the warps in snake order (offset r*W + w for even r, r*W + W-1-w for odd r), so
-    // that every warp carries the same number of tile updates over a full wave (row o has o columns inside it).
-    auto off_of = [&](int r) { return r * W_ + ((r & 1) ? (W_ - 1 - warp) : warp); };
-    auto wave_R = [&](int c) {
-        const int m = wend(c) - wstart(c);
-        int R = 0;
-        for (int r = 0; r < E3_R; ++r) R += (off_of(r) < m) ? 1 : 0;
-        return R;
-    };
-    auto row_of = [&](int c, int r) { return wstart(c) + off_of(r); };   // r-th row of this warp in wave c, ascending
-    auto make_sv = [&](int c, int j, int part) {
-        SV v;
-        v.valid = 1; v.c = c; v.j = j; v.part = part;
-        v.R = wave_R(c); v.base = wstart(c);
-        int below = 0;
-        for (int r = 0; r < E3_R; ++r) below += (r < v.R && row_of(c, r) <= j) ? 1 : 0;
-        v.nact = v.R - below;
-        v.split = (v.nact > 0 && row_of(c, v.R - v.nact) == j + 1) ? 1 : 0;   // my smallest active row is row j+1
-        if (part == 0) { v.s_lo = v.split ? v.nact - 1 : 0; v.cnt = v.split ? 1 : v.nact; }
-        else { v.s_lo = 0; v.cnt = v.nact - 1; }
-        return v;
-    };
-    auto first_sv = [&](int c, int j) {   // first (sub)visit at or after column j of wave c
-        while (c < nwaves) {
-            const int R = wave_R(c);
-            if (R > 0 && j <= row_of(c, R - 1) - 1) return make_sv(c, j, 0);
-            ++c; j = 0;
-        }
-        SV v; v.valid = 0; v.c = nwaves; v.j = 0; v.part = 0; v.split = 0; v.nact = 0; v.s_lo = 0; v.cnt = 0; v.R = 0; v.base = 0;
-        return v;
-    };
-    auto next_sv = [&](const SV& v) {
-        if (v.part == 0 && v.split && v.nact > 1) return make_sv(v.c, v.j, 1);
-        return first_sv(v.c, v.j + 1);
-    };
-    // tile addresses of a (sub)visit are computed once (by lane 0) and reused for its four quarter steps
-    struct TP { const float* p[E3_R]; const float* solo; };
-    auto tile_ptrs = [&](const SV& v) {
-        TP t;
-        t.solo = nullptr;
-#pragma unroll
-        for (int sl = 0; sl < E3_R; ++sl) {
-            const int i = row_of(v.c, v.R - 1 - sl);
-            t.p[sl] = (sl >= v.s_lo && sl < v.s_lo + v.cnt) ? tiles + (size_t)tile_index(i, v.j, nb) * GPIS_TILE_ELEMS : nullptr;
-            if (sl == v.s_lo) t.solo = t.p[sl];   // static index: keeps the array in registers
-        }
-        return t;
+    struct SV { int valid, c, j, part, split, s_lo, cnt, solo_tile, t0, t1, t2, t3; };
+    const int4* prog = G.recs + G.off[nb * E3_WARPS + warp];
+    const int nwaves = prog[0].x;
+    const int4* pvis = prog + 2 + 2 * nwaves;
+    auto load_sv = [&](int v) {
+        const int4 a = __ldg(pvis + 2 * v), b = __ldg(pvis + 2 * v + 1);
+        SV r;
+        r.j = a.x;
+        r.s_lo = a.y & 7; r.cnt = (a.y >> 3) & 7; r.part = (a.y >> 6) & 1; r.split = (a.y >> 7) & 1; r.valid = (a.y >> 8) & 1;
+        r.c = (a.y >> 16) & 255;
+        r.solo_tile = a.z;
+        r.t0 = b.x; r.t1 = b.y; r.t2 = b.z; r.t3 = b.w;
+        return r;
     };
 #ifdef E3_USE_CPASYNC
     // cp.async (LDGSTS): every lane moves 2 x 16 B per quarter tile. Measured faster than 1 KB TMA bulk copies for
     // this access pattern (profiles/r01). The lookahead part of a split visit (one row, R = 1 work) fetches its
     // whole 4 KB tile at once: its four quarter steps are too short to hide a load each.
-    auto issue = [&](const SV& v, const TP& t, int q, int stage) {
+    auto issue = [&](const SV& v, int q, int stage) {
         if (v.part == 0 && v.split) {
-            const float* src = t.solo + lane * 4;
+            const float* src = tiles + (size_t)v.solo_tile * GPIS_TILE_ELEMS + lane * 4;
             float* dst = stg + stage * E3_STAGE_FLOATS + lane * 4;
 #pragma unroll
             for (int h = 0; h < 8; ++h)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + h * 128)), "l"(src + h * 128) : "memory");
         } else {
 #pragma unroll
-            for (int sl = 0; sl < E3_R; ++sl)
-                if (t.p[sl]) {
-                    const float* src = t.p[sl] + q * 256 + lane * 4;
+            for (int sl = 0; sl < E3_R; ++sl) {
+                const int ti = sl == 0 ? v.t0 : sl == 1 ? v.t1 : sl == 2 ? v.t2 : v.t3;
+                if (ti >= 0) {
+                    const float* src = tiles + (size_t)ti * GPIS_TILE_ELEMS + q * 256 + lane * 4;
                     float* dst = stg + (stage * E3_R + sl) * 256 + lane * 4;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 128)), "l"(src + 128) : "memory");
                 }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #else
-    auto issue = [&](const SV& v, const TP& t, int q, int stage) {
+    auto issue = [&](const SV& v, int q, int stage) {
         if (lane != 0) return;
         if (v.part == 0 && v.split) {
             mbar_expect_tx(&bars[stage], GPIS_TILE_BYTES);
-            tma_load_1d(stg + stage * E3_STAGE_FLOATS, t.solo, GPIS_TILE_BYTES, &bars[stage]);
+            tma_load_1d(stg + stage * E3_STAGE_FLOATS, tiles + (size_t)v.solo_tile * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[stage]);
             return;
         }
         mbar_expect_tx(&bars[stage], (uint32_t)v.cnt * 1024u);
 #pragma unroll
-        for (int sl = 0; sl < E3_R; ++sl)
-            if (t.p[sl]) tma_load_1d(stg + (stage * E3_R + sl) * 256, t.p[sl] + q * 256, 1024u, &bars[stage]);
+        for (int sl = 0; sl < E3_R; ++sl) {
+            const int ti = sl == 0 ? v.t0 : sl == 1 ? v.t1 : sl == 2 ? v.t2 : v.t3;
+            if (ti >= 0) tma_load_1d(stg + (stage * E3_R + sl) * 256, tiles + (size_t)ti * GPIS_TILE_ELEMS + q * 256, 1024u, &bars[stage]);
+        }
     };
 #endif
 
     float acc[E3_R][4][CPL];
     uint32_t ph = 0;
     int st = 0;
-    SV cur = first_sv(0, 0);
-    TP curp = tile_ptrs(cur);
-    if (cur.valid) issue(cur, curp, 0, 0);
+    int vi = 0;
+    SV cur = load_sv(0);
+    if (cur.valid) issue(cur, 0, 0);
     if (tid == 0) mbar_arrive(&ready[0]);   // row 0 has nothing to eliminate: B_0 is U_0
 
     for (int c = 0; c < nwaves; ++c) {
-        const int R = wave_R(c);
+        const int R = __ldg(prog + 2 + 2 * c).x;
         if (R == 0) continue;
         // accumulators <- right-hand sides of this warp's rows (slot s = its (R-1-s)-th row, ascending)
+        {
+            const int4 rows = __ldg(prog + 3 + 2 * c);
 #pragma unroll
-        for (int r = 0; r < E3_R; ++r) {
-            if (r < R) {
-                const float* Ui = U + (size_t)row_of(c, R - 1 - r) * 32 * NCOL;
+            for (int r = 0; r < E3_R; ++r) {
+                if (r < R) {
+                    const int row = r == 0 ? rows.x : r == 1 ? rows.y : r == 2 ? rows.z : rows.w;
+                    const float* Ui = U + (size_t)row * 32 * NCOL;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    ld_cols<CPL>(Ui + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
+                    for (int i = 0; i < 4; ++i)
+                        ld_cols<CPL>(Ui + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
+                }
             }
         }
         while (cur.valid && cur.c == c) {
-            const SV nxt = next_sv(cur);
-            const TP nxtp = tile_ptrs(nxt);
+            const SV nxt = load_sv(vi + 1);
             // operand U_j must be final (published by the owner of row j)
             E3_T(t_r0)
             if (cur.part == 0) mbar_wait(&ready[cur.j], 0u);   // hardware-suspended wait, acquire semantics
@@ -416,8 +470,8 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 const bool do_wait = !solo || q == 0;
                 if (do_wait) {
                     bool issued = true;
-                    if (!solo && q < 3) issue(cur, curp, q + 1, st ^ 1);
-                    else if (nxt.valid) issue(nxt, nxtp, 0, st ^ 1);
+                    if (!solo && q < 3) issue(cur, q + 1, st ^ 1);
+                    else if (nxt.valid) issue(nxt, 0, st ^ 1);
                     else issued = false;
 #ifdef E3_USE_CPASYNC
                     if (issued) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -445,7 +499,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                     g_e3_timing[warp * 32 + 16 + cur.cnt] += t_s2 - t_s1; g_e3_timing[warp * 32 + 24 + cur.cnt] += 1; }
 #endif
             }
-            if (cur.part == 0 && cur.split) {
+            if (solo) {
                 // row j+1 (slot s_lo) is final: publish it
                 float* Un = U + (size_t)(cur.j + 1) * 32 * NCOL;
 #pragma unroll
@@ -460,7 +514,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 if (lane == 0) mbar_arrive(&ready[cur.j + 1]);   // release: the stores above are visible to waiters
             }
             cur = nxt;
-            curp = nxtp;
+            ++vi;
         }
     }
     E3_T(t_elim1)
@@ -475,10 +529,15 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     for (int c = 0; c < CPL; ++c) ss[c] = 0.f;
     {
         static_assert(E3_R == 4, "a stage must hold one full tile");
-        // owned rows in order: wave c, r = 0 .. wave_R(c)-1
+        // owned rows in order: wave c, slots R-1 .. 0 (ascending rows)
         auto next_owned = [&](int& c, int& r) {   // advance (c, r) to the next owned row; returns -1 at the end
             while (c < nwaves) {
-                if (r < wave_R(c)) return row_of(c, r);
+                const int R = __ldg(prog + 2 + 2 * c).x;
+                if (r < R) {
+                    const int4 rows = __ldg(prog + 3 + 2 * c);
+                    const int sl = R - 1 - r;
+                    return sl == 0 ? rows.x : sl == 1 ? rows.y : sl == 2 ? rows.z : rows.w;
+                }
                 ++c; r = 0;
             }
             return -1;
@@ -567,7 +626,7 @@ static inline int query_eval_init(std::string& err) {
 static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable& T, const QueryParams& P,
                              const QueryWork& W, int npairs, int nslots, int max_nb, int32_t** d_sort,
                              int64_t* sort_cap, int64_t* launches, std::string& err, double* d_acc, int version,
-                             int64_t* items_out = nullptr) {
+                             const EvalProg& G, int64_t* items_out = nullptr) {
 #define CK2(call)                                                                 \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -629,17 +688,17 @@ static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable&
     if (items_out) { items_out[0] += tot[1]; items_out[1] += tot[4]; items_out[2] += tot[2]; items_out[3] += tot[3]; }
     if (tot[1] > 0) {
         const int nbm = max_nb < E3_NB_A ? max_nb : E3_NB_A;
-        k_eval_v3<8><<<tot[1], E3_THREADS, Eval3Smem::total(nbm, 32), st>>>(d_x, T, P, W, S, S.items);
+        k_eval_v3<8><<<tot[1], E3_THREADS, Eval3Smem::total(nbm, 32), st>>>(d_x, T, P, W, S, S.items, G);
         *launches += 1;
     }
     if (tot[4] > 0) {
         const int nbm = max_nb < E3_NB_M ? max_nb : E3_NB_M;
-        k_eval_v3<6><<<tot[4], E3_THREADS, Eval3Smem::total(nbm, 24), st>>>(d_x, T, P, W, S, S.itemsM);
+        k_eval_v3<6><<<tot[4], E3_THREADS, Eval3Smem::total(nbm, 24), st>>>(d_x, T, P, W, S, S.itemsM, G);
         *launches += 1;
     }
     if (tot[2] > 0) {
         const int nbm = max_nb < E3_NB_B ? max_nb : E3_NB_B;
-        k_eval_v3<4><<<tot[2], E3_THREADS, Eval3Smem::total(nbm, 16), st>>>(d_x, T, P, W, S, S.itemsB);
+        k_eval_v3<4><<<tot[2], E3_THREADS, Eval3Smem::total(nbm, 16), st>>>(d_x, T, P, W, S, S.itemsB, G);
         *launches += 1;
     }
     if (tot[3] > 0) {
