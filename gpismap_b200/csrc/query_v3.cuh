@@ -17,6 +17,7 @@
 #pragma once
 #include <algorithm>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -171,17 +172,21 @@ __device__ __forceinline__ void qmma_dispatch(int nact, float (&acc)[E3_R][4][CP
 // once on the host (same rules the kernel used to evaluate inline: waves of E3_WAVE block rows, the partial
 // wave first, snake dealing, split visits for the lookahead) and read by the kernel as a table: two int4 per
 // record, uniform loads, no per-visit index arithmetic on the device.
-//   header  : {nwaves, nvisits, 0, 0}, {0,0,0,0}
+//   header  : {nwaves, nvisits, nvar, 0}, {0,0,0,0}
 //   wave c  : {R, 0, 0, 0}, {row of slot 0, 1, 2, 3}                 (slot s = the warp's (R-1-s)-th row, ascending)
 //   visit v : {j, flags, solo tile, nact}, {tile of slot 0, 1, 2, 3}   (tile = index into the leaf's tile array, -1 = idle)
 //             flags: bits 0-2 s_lo, 3-5 cnt, 6 part, 7 split, 8 valid, 16-23 wave
+//   4 terminator visits (valid clear), then the rows whose variance product this warp computes, 4 per record
 struct EvalProg {
     const int4* recs;       // all programs
     const int32_t* off;     // [E3_PROG_MAXNB + 1][E3_WARPS] record offset of (nb, warp)
 };
 #define E3_PROG_MAXNB 80
 
-static inline void e3_build_program(int nb, int warp, std::vector<int4>& out) {
+struct E3Visit { int j, s_lo, cnt, part, split, c, nact, t[4]; };
+struct E3WarpProg { int nwaves; int R[8]; int rows[8][4]; std::vector<E3Visit> vis; std::vector<int> var_rows; };
+
+static inline void e3_build_warp(int nb, int warp, E3WarpProg& wp) {
     const int W_ = E3_WARPS;
     const int nwaves = (nb + E3_WAVE - 1) / E3_WAVE;
     const int first_rows = (nb % E3_WAVE) ? (nb % E3_WAVE) : E3_WAVE;
@@ -195,17 +200,13 @@ static inline void e3_build_program(int nb, int warp, std::vector<int4>& out) {
         return R;
     };
     auto row_of = [&](int c, int r) { return wstart(c) + off_of(r); };
-    const size_t head = out.size();
-    out.push_back(make_int4(nwaves, 0, 0, 0));
-    out.push_back(make_int4(0, 0, 0, 0));
+    wp.nwaves = nwaves;
+    wp.vis.clear(); wp.var_rows.clear();
     for (int c = 0; c < nwaves; ++c) {
         const int R = wave_R(c);
-        int rows[4] = {-1, -1, -1, -1};
-        for (int sl = 0; sl < R; ++sl) rows[sl] = row_of(c, R - 1 - sl);
-        out.push_back(make_int4(R, 0, 0, 0));
-        out.push_back(make_int4(rows[0], rows[1], rows[2], rows[3]));
+        wp.R[c] = R;
+        for (int sl = 0; sl < 4; ++sl) wp.rows[c][sl] = (sl < R) ? row_of(c, R - 1 - sl) : -1;
     }
-    int nvis = 0;
     for (int c = 0; c < nwaves; ++c) {
         const int R = wave_R(c);
         if (R == 0) continue;
@@ -217,32 +218,98 @@ static inline void e3_build_program(int nb, int warp, std::vector<int4>& out) {
             if (nact <= 0) break;
             const bool split = row_of(c, R - nact) == j + 1;
             for (int part = 0; part < 2; ++part) {
-                int s_lo, cnt;
-                if (part == 0) { s_lo = split ? nact - 1 : 0; cnt = split ? 1 : nact; }
-                else { if (!(split && nact > 1)) break; s_lo = 0; cnt = nact - 1; }
-                int t[4] = {-1, -1, -1, -1};
-                for (int sl = 0; sl < E3_R; ++sl)
-                    if (sl >= s_lo && sl < s_lo + cnt) t[sl] = tile_index(row_of(c, R - 1 - sl), j, nb);
-                const int flags = s_lo | (cnt << 3) | (part << 6) | ((split ? 1 : 0) << 7) | (1 << 8) | (c << 16);
-                out.push_back(make_int4(j, flags, t[s_lo], nact));
-                out.push_back(make_int4(t[0], t[1], t[2], t[3]));
-                ++nvis;
+                E3Visit v;
+                if (part == 0) { v.s_lo = split ? nact - 1 : 0; v.cnt = split ? 1 : nact; }
+                else { if (!(split && nact > 1)) break; v.s_lo = 0; v.cnt = nact - 1; }
+                v.j = j; v.part = part; v.split = split ? 1 : 0; v.c = c; v.nact = nact;
+                for (int sl = 0; sl < 4; ++sl)
+                    v.t[sl] = (sl >= v.s_lo && sl < v.s_lo + v.cnt) ? tile_index(row_of(c, R - 1 - sl), j, nb) : -1;
+                wp.vis.push_back(v);
             }
         }
     }
-    out.push_back(make_int4(0, 0, -1, 0));   // terminator: valid bit clear
-    out.push_back(make_int4(-1, -1, -1, -1));
-    out[head].y = nvis;
+}
+
+// Which warp computes the variance product V_j = Dinv(j) U_j of which row: a static list schedule on a coarse
+// timing model of the elimination (visit costs measured with scripts/timing_probe.py), so that the warps which
+// finish their elimination early take the rows of the warps that carry the end of the dependency chain.
+static inline void e3_assign_variance(int nb, E3WarpProg (&wp)[E3_WARPS]) {
+    const double cost[5] = {0., 3800., 5100., 7000., 7700.};   // cycles per visit by active slots (incl. control)
+    const double pub = 300., cvar = 3600.;
+    std::vector<double> ready(nb, -1.);
+    ready[0] = 0.;
+    double t[E3_WARPS];
+    size_t pc[E3_WARPS];
+    for (int w = 0; w < E3_WARPS; ++w) { t[w] = 0.; pc[w] = 0; }
+    bool progress = true;
+    while (progress) {
+        progress = false;
+        for (int w = 0; w < E3_WARPS; ++w) {
+            while (pc[w] < wp[w].vis.size()) {
+                const E3Visit& v = wp[w].vis[pc[w]];
+                if (v.part == 0) {
+                    if (ready[v.j] < 0.) break;
+                    t[w] = std::max(t[w], ready[v.j]);
+                }
+                t[w] += cost[v.cnt];
+                if (v.part == 0 && v.split) ready[v.j + 1] = t[w] + pub;
+                ++pc[w];
+                progress = true;
+            }
+        }
+    }
+    double avail[E3_WARPS];
+    for (int w = 0; w < E3_WARPS; ++w) avail[w] = t[w];
+    std::vector<int> order(nb);
+    for (int j = 0; j < nb; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ready[a] < ready[b]; });
+    for (int j : order) {
+        int best = 0;
+        double bt = 1e300;
+        for (int w = 0; w < E3_WARPS; ++w) {
+            const double s = std::max(avail[w], ready[j]);
+            if (s < bt) { bt = s; best = w; }
+        }
+        avail[best] = bt + cvar;
+        wp[best].var_rows.push_back(j);
+    }
+}
+
+static inline void e3_emit_program(const E3WarpProg& wp, std::vector<int4>& out) {
+    out.push_back(make_int4(wp.nwaves, (int)wp.vis.size(), (int)wp.var_rows.size(), 0));
+    out.push_back(make_int4(0, 0, 0, 0));
+    for (int c = 0; c < wp.nwaves; ++c) {
+        out.push_back(make_int4(wp.R[c], 0, 0, 0));
+        out.push_back(make_int4(wp.rows[c][0], wp.rows[c][1], wp.rows[c][2], wp.rows[c][3]));
+    }
+    for (const E3Visit& v : wp.vis) {
+        const int flags = v.s_lo | (v.cnt << 3) | (v.part << 6) | (v.split << 7) | (1 << 8) | (v.c << 16);
+        out.push_back(make_int4(v.j, flags, v.t[v.s_lo], v.nact));
+        out.push_back(make_int4(v.t[0], v.t[1], v.t[2], v.t[3]));
+    }
+    for (int k = 0; k < 4; ++k) {   // terminators (valid bit clear); also the landing zone of the look-ahead loads
+        out.push_back(make_int4(0, 0, -1, 0));
+        out.push_back(make_int4(-1, -1, -1, -1));
+    }
+    for (size_t i = 0; i < wp.var_rows.size(); i += 4) {
+        int r[4] = {-1, -1, -1, -1};
+        for (size_t k = 0; k < 4 && i + k < wp.var_rows.size(); ++k) r[k] = wp.var_rows[i + k];
+        out.push_back(make_int4(r[0], r[1], r[2], r[3]));
+    }
 }
 // all (nb, warp) programs -> device
 static inline int e3_upload_programs(int4** d_recs, int32_t** d_off, std::string& err) {
     std::vector<int4> recs;
     std::vector<int32_t> off((E3_PROG_MAXNB + 1) * E3_WARPS, 0);
-    for (int nb = 1; nb <= E3_PROG_MAXNB; ++nb)
+    for (int nb = 1; nb <= E3_PROG_MAXNB; ++nb) {
+        E3WarpProg wp[E3_WARPS];
+        for (int w = 0; w < E3_WARPS; ++w) e3_build_warp(nb, w, wp[w]);
+        e3_assign_variance(nb, wp);
         for (int w = 0; w < E3_WARPS; ++w) {
             off[nb * E3_WARPS + w] = (int32_t)recs.size();
-            e3_build_program(nb, w, recs);
+            e3_emit_program(wp[w], recs);
         }
+    }
     cudaError_t e = cudaMalloc(d_recs, recs.size() * sizeof(int4));
     if (e == cudaSuccess) e = cudaMalloc(d_off, off.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(*d_recs, recs.data(), recs.size() * sizeof(int4), cudaMemcpyHostToDevice);
@@ -317,32 +384,43 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     }
     __syncthreads();
     const float* xq_s = park ? s_xq : red;
-    for (int idx = tid; idx < N * QBT; idx += E3_THREADS) {
-        const int qi = idx % QBT, k = idx / QBT;
-        if (qi >= cnt) continue;
-        float xq[3] = {xq_s[4 * qi], xq_s[4 * qi + 1], xq_s[4 * qi + 2]};
-        const float4 p = park ? s_pts[k] : pts[k];
-        const int g = __float_as_int(p.w);
-        const float xs[3] = {p.x, p.y, p.z};
-        float d[3], s2 = 0.f;
-        for (int c = 0; c < dim; ++c) { d[c] = xs[c] - xq[c]; s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c]; }
-        const float r = sqrtf(s2);
-        const DF e = exp_df(-P.a * r);
-        float* col = U + 4 * qi;
-        col[k * NCOL] = kf_val(r, P.a, e);
-        float k1[3];
-        for (int c = 0; c < dim; ++c) { k1[c] = kf1_val(d[c], P.a, e); col[k * NCOL + 1 + c] = k1[c]; }
-        if (g >= 0) {
-            for (int c = 0; c < dim; ++c) {
-                const int row = N + c * ng + g;
-                col[row * NCOL] = -k1[c];
-                for (int e2 = 0; e2 < dim; ++e2) {
-                    const int c0 = min(c, e2), e0 = max(c, e2);
-                    col[row * NCOL + 1 + e2] = kf2_val(r, d[c0], d[e0], c == e2 ? 1.f : 0.f, P.a, e);
+    // dimension-specialised (fully unrolled, no local arrays): this loop is 8-14 % of the kernel for small leaves
+    auto kstar = [&](auto dimc) {
+        constexpr int DIM = decltype(dimc)::value;
+        for (int idx = tid; idx < N * QBT; idx += E3_THREADS) {
+            const int qi = idx % QBT, k = idx / QBT;
+            if (qi >= cnt) continue;
+            const float4 p = park ? s_pts[k] : pts[k];
+            const int g = __float_as_int(p.w);
+            const float xs[3] = {p.x, p.y, p.z};
+            float d[DIM], s2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) { d[c] = xs[c] - xq_s[4 * qi + c]; s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c]; }
+            const float r = sqrtf(s2);
+            const DF e = exp_df(-P.a * r);
+            float* col = U + 4 * qi;
+            col[k * NCOL] = kf_val(r, P.a, e);
+            float k1[DIM];
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) { k1[c] = kf1_val(d[c], P.a, e); col[k * NCOL + 1 + c] = k1[c]; }
+            if (g >= 0) {
+                float k2[DIM][DIM];   // symmetric: (c, e2) and (e2, c) are the same expression (covFnc.cpp:300-309)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c)
+#pragma unroll
+                    for (int e2 = c; e2 < DIM; ++e2) k2[c][e2] = k2[e2][c] = kf2_val(r, d[c], d[e2], c == e2 ? 1.f : 0.f, P.a, e);
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    float* rowp = col + (size_t)(N + c * ng + g) * NCOL;
+                    rowp[0] = -k1[c];
+#pragma unroll
+                    for (int e2 = 0; e2 < DIM; ++e2) rowp[1 + e2] = k2[c][e2];
                 }
             }
         }
-    }
+    };
+    if (dim == 3) kstar(std::integral_constant<int, 3>{});
+    else kstar(std::integral_constant<int, 2>{});
     __syncthreads();
 
     // ---- mean: U^T alpha (OnGPIS.cpp:187); lane = column, warps split the rows
@@ -456,6 +534,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         }
         while (cur.valid && cur.c == c) {
             const SV nxt = load_sv(vi + 1);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pvis + 2 * (vi + 4)));   // program records: 4 visits per line
             // operand U_j must be final (published by the owner of row j)
             E3_T(t_r0)
             if (cur.part == 0) mbar_wait(&ready[cur.j], 0u);   // hardware-suspended wait, acquire semantics
@@ -521,27 +600,17 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     E3_T(t_elim2)
     E3_ACC(4, t_elim0, t_elim1)   // whole elimination of this warp
 
-    // ---- V_j = Dinv(j) U_j and the column sums of V^2 (OnGPIS.cpp:200-201) for the rows THIS warp owns: they are
-    // final and were written to shared memory by this warp itself, so no block-wide barrier is needed and a warp
-    // that finishes its elimination early starts here while the others are still eliminating.
+    // ---- V_j = Dinv(j) U_j and the column sums of V^2 (OnGPIS.cpp:200-201) for the rows the program assigns to
+    // this warp; each row is waited for individually (ready[j]), so there is no block-wide barrier and a warp that
+    // finishes its elimination early works here while the others are still eliminating.
     float ss[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) ss[c] = 0.f;
     {
         static_assert(E3_R == 4, "a stage must hold one full tile");
-        // owned rows in order: wave c, slots R-1 .. 0 (ascending rows)
-        auto next_owned = [&](int& c, int& r) {   // advance (c, r) to the next owned row; returns -1 at the end
-            while (c < nwaves) {
-                const int R = __ldg(prog + 2 + 2 * c).x;
-                if (r < R) {
-                    const int4 rows = __ldg(prog + 3 + 2 * c);
-                    const int sl = R - 1 - r;
-                    return sl == 0 ? rows.x : sl == 1 ? rows.y : sl == 2 ? rows.z : rows.w;
-                }
-                ++c; r = 0;
-            }
-            return -1;
-        };
+        // rows assigned to this warp by the program (not necessarily its own: see e3_assign_variance)
+        const int nvar = prog[0].z;
+        const int* vrows = reinterpret_cast<const int*>(pvis + 2 * (prog[0].y + 4));
         auto issue_d = [&](int j, int s2) {
             if (lane == 0) {
                 mbar_expect_tx(&bars[s2], GPIS_TILE_BYTES);
@@ -552,13 +621,14 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
 #endif
-        int vc = 0, vr = 0;
-        int j = next_owned(vc, vr);
+        int vk = 0;
+        int j = (vk < nvar) ? __ldg(vrows + vk) : -1;
         if (j >= 0) issue_d(j, st);
         while (j >= 0) {
-            ++vr;
-            const int jn = next_owned(vc, vr);
+            ++vk;
+            const int jn = (vk < nvar) ? __ldg(vrows + vk) : -1;
             if (jn >= 0) issue_d(jn, st ^ 1);
+            mbar_wait(&ready[j], 0u);   // U_j final (acquire); rows of other warps may still be in flight
             mbar_wait(&bars[st], (ph >> st) & 1u);
             ph ^= (1u << st);
             float v[E3_R][4][CPL];
