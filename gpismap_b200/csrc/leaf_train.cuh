@@ -56,36 +56,43 @@ struct TrainSmem {
 };
 
 // acc[i][j] -= sum_k A[k][4*rg+i] * B[k][8*cg+j]   (A, B: k-major 32x32 tiles in shared memory)
-__device__ __forceinline__ void tile_mma_sub(float (&acc)[4][8], const float* __restrict__ A,
-                                             const float* __restrict__ B, int rg, int cg) {
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(A + k * 32 + 4 * rg);
-        const float4 b0 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg);
-        const float4 b1 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg + 4);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+// Packed FFMA2 along j; the operands of step k+1 are loaded before the FMAs of step k issue.
+template <bool SUB>
+__device__ __forceinline__ void tile_mma(float (&acc)[4][8], const float* __restrict__ A,
+                                         const float* __restrict__ B, int rg, int cg) {
+    const float* Ap = A + 4 * rg;
+    const float* Bp = B + 8 * cg;
+    float4 a[2], b0[2], b1[2];
+    a[0] = *reinterpret_cast<const float4*>(Ap);
+    b0[0] = *reinterpret_cast<const float4*>(Bp);
+    b1[0] = *reinterpret_cast<const float4*>(Bp + 4);
+#pragma unroll 4
+    for (int k2 = 0; k2 < 32; k2 += 2) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int h = 0; h < 2; ++h) {
+            const int k = k2 + h, cu = h, nx = h ^ 1;
+            if (k + 1 < 32) {
+                a[nx] = *reinterpret_cast<const float4*>(Ap + (k + 1) * 32);
+                b0[nx] = *reinterpret_cast<const float4*>(Bp + (k + 1) * 32);
+                b1[nx] = *reinterpret_cast<const float4*>(Bp + (k + 1) * 32 + 4);
+            }
+            const float av[4] = {a[cu].x, a[cu].y, a[cu].z, a[cu].w};
+            const float bv[8] = {b0[cu].x, b0[cu].y, b0[cu].z, b0[cu].w, b1[cu].x, b1[cu].y, b1[cu].z, b1[cu].w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(-av[i], bv[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    if (SUB) fma2_sub(acc[i][j], acc[i][j + 1], bv[j], bv[j + 1], av[i]);
+                    else fma2_add(acc[i][j], acc[i][j + 1], bv[j], bv[j + 1], av[i]);
+                }
+        }
     }
 }
-// acc[i][j] += sum_k A[k][4*rg+i] * B[k][8*cg+j]
-__device__ __forceinline__ void tile_mma_add(float (&acc)[4][8], const float* __restrict__ A,
-                                             const float* __restrict__ B, int rg, int cg) {
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(A + k * 32 + 4 * rg);
-        const float4 b0 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg);
-        const float4 b1 = *reinterpret_cast<const float4*>(B + k * 32 + 8 * cg + 4);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
+__device__ __forceinline__ void tile_mma_sub(float (&acc)[4][8], const float* __restrict__ A, const float* __restrict__ B, int rg, int cg) {
+    tile_mma<true>(acc, A, B, rg, cg);
+}
+__device__ __forceinline__ void tile_mma_add(float (&acc)[4][8], const float* __restrict__ A, const float* __restrict__ B, int rg, int cg) {
+    tile_mma<false>(acc, A, B, rg, cg);
 }
 // store / load a lane's 4x8 block to a k-major tile: element (r, c) at c*32 + r
 __device__ __forceinline__ void tile_store(float* T, const float (&acc)[4][8], int rg, int cg) {

@@ -75,7 +75,7 @@ struct GPisMap3::Impl {
         const int m = (int)vu.size() / 2;
         val.assign(m, 0.f);
         var.assign(m, 0.f);
-        if (m > 0) gpis_obs_test(core.ctx, vu.data(), 2, m, val.data(), var.data());
+        if (m > 0) { ProfScope ps(0); gpis_obs_test(core.ctx, vu.data(), 2, m, val.data(), var.data()); }
     }
 
     struct ReEval {            // per-sample state between the two observation batches
@@ -349,6 +349,7 @@ void GPisMap3::Impl::updateMapPoints() {
     if (!core.tree || !obs_ready) return;
     auto* tree = core.tree;
     std::vector<int> oc;
+    double tp0 = now_s();
     tree->query_clusters(pose_tr.data(), range_obs_max, oc);
     if (oc.empty()) return;
     const float r2 = range_obs_max * range_obs_max;
@@ -378,6 +379,7 @@ void GPisMap3::Impl::updateMapPoints() {
         if (within_angle == 0) continue;
         inview.push_back(LeafHandle{cid, n.gen});
     }
+    g_prof_s[1] += now_s() - tp0; g_prof_n[1] += 1; tp0 = now_s();
     // Pre-compute both observation batches for every sample currently under an in-view leaf.
     std::vector<int> ids_all;
     for (const LeafHandle& h : inview) tree->collect_samples(h.cell, ids_all);
@@ -393,6 +395,8 @@ void GPisMap3::Impl::updateMapPoints() {
             if (st[i].alive1) { pre_probe[i] = probe; probe += 6; }
         }
     }
+    g_prof_s[2] += now_s() - tp0; g_prof_n[2] += 1;
+    ProfScope ps3(3);
     // Serial pass in the reference's order. Samples created during this pass (a fused point that
     // landed in a leaf not yet visited) are evaluated on demand, leaf by leaf.
     std::vector<int> ids, fresh;
@@ -452,6 +456,7 @@ void GPisMap3::Impl::evalPoints() {
     obs_test(vup, rinv0p, varp);
 
     std::vector<int> touched, freed;
+    ProfScope ps4(4);
     for (int k = 0; k < K; k++) {
         const int k3 = 3 * k;
         if (varc[k] > setting.obs_var_thre) continue;

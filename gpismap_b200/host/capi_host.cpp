@@ -6,6 +6,7 @@
 
 #include "gpismap/GPisMap.h"
 #include "gpismap/GPisMap3.h"
+#include "map_core.hpp"
 
 extern "C" {
 
@@ -54,6 +55,10 @@ int gm3_leaves(void* m, float* centres, int* counts, int cap) {
 }
 int gm3_insert_samples(void* m, const float* s, int n) { return ((GPisMap3*)m)->insertSamples(s, n); }
 int gm3_train_active(void* m) { return ((GPisMap3*)m)->trainActive(); }
+// development aid: coarse host profile (map_core.hpp), read and reset
+void gm_profile(double* secs16, long long* calls16) {
+    for (int i = 0; i < 16; ++i) { secs16[i] = gpismap_host::g_prof_s[i]; calls16[i] = gpismap_host::g_prof_n[i]; gpismap_host::g_prof_s[i] = 0; gpismap_host::g_prof_n[i] = 0; }
+}
 void gm3_timing(void* m, double* phases5, int* counts3, float* train_ms) {
     const GPisMap3Timing& t = ((GPisMap3*)m)->lastTiming();
     for (int i = 0; i < 5; ++i) phases5[i] = t.phase[i];

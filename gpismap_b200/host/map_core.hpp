@@ -23,6 +23,17 @@ inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Coarse host-side profile (development aid, scripts/update_profile.py): seconds and call counts per slot.
+//  0 gpis_obs_test  1 updateMapPoints: cull  2 updateMapPoints: collect+stage  3 updateMapPoints: serial apply
+//  4 evalPoints: serial insert  5 train_active: dirty set  6 train_active: gather  7 gpis_leaves_update  8 sync_table
+inline double g_prof_s[16] = {0};
+inline long long g_prof_n[16] = {0};
+struct ProfScope {
+    int slot; double t0;
+    explicit ProfScope(int s) : slot(s), t0(now_s()) {}
+    ~ProfScope() { g_prof_s[slot] += now_s() - t0; g_prof_n[slot] += 1; }
+};
+
 struct LeafHandle {
     int cell; uint32_t gen;
     bool operator<(const LeafHandle& o) const { return cell < o.cell || (cell == o.cell && gen < o.gen); }
@@ -112,6 +123,7 @@ public:
         if (!tree || !ctx) { active.clear(); return false; }
         std::set<int> update_set;
         std::vector<int> qs;
+        double tp0 = now_s();
         for (const LeafHandle& h : active) {
             if (!tree->cell_alive(h.cell, h.gen)) continue;
             update_set.insert(h.cell);
@@ -121,6 +133,7 @@ public:
             for (int q : qs) update_set.insert(q);
         }
         active.clear();                                           // GPisMap3.cpp:789
+        g_prof_s[5] += now_s() - tp0; g_prof_n[5] += 1; tp0 = now_s();
         std::vector<int32_t> cells;
         std::vector<float> centres;
         std::vector<int32_t> offsets(1, 0);
@@ -146,7 +159,9 @@ public:
             device_cells[pack(cc)] = {cc[0], cc[1], cc[2]};
         }
         const int nl = (int)offsets.size() - 1;
+        g_prof_s[6] += now_s() - tp0; g_prof_n[6] += 1;
         if (nl > 0) {
+            ProfScope ps(7);
             const int rc = gpis_leaves_update(ctx, nl, cells.data(), centres.data(), offsets.data(), samples.data(), nullptr);
             if (rc != GPIS_OK) {
                 std::fprintf(stderr, "gpismap_b200: gpis_leaves_update failed (%d): %s\n", rc, gpis_last_error(ctx));
@@ -164,6 +179,7 @@ public:
     // everything, octree.cpp:829-859) and tell it the root box.
     bool sync_table() {
         if (!tree || !ctx) return false;
+        ProfScope ps(8);
         std::vector<int> all;
         float zero[D];
         for (int a = 0; a < D; ++a) zero[a] = 0.f;

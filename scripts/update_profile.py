@@ -1,0 +1,28 @@
+"""Development aid: per-phase timing of GPisMap3::update over the bench's synthetic frames."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gpismap_b200 import hostapi, synth
+nf = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+m = hostapi.GPisMap3()
+rows = []
+for k in range(nf):
+    dz, pose = synth.frame(k, nf)
+    t0 = time.perf_counter(); m.update(dz, pose); dt = time.perf_counter() - t0
+    ph, cnt, ms = m.timing()
+    rows.append(list(ph * 1e3) + [dt * 1e3, ms] + list(cnt))
+import ctypes as C
+L = hostapi.lib()
+secs = np.zeros(16); calls = np.zeros(16, np.int64)
+L.gm_profile(secs.ctypes.data_as(C.c_void_p), calls.ctypes.data_as(C.c_void_p))
+a = np.array(rows)
+names = ["preproc", "regressObs", "updateMapPoints", "addNewMeas+eval", "trainActive", "total", "train_kernel", "valid_px", "active", "trained"]
+print("median / p90 / max over", nf, "frames (ms)")
+for i, n in enumerate(names):
+    print(f"{n:18s} {np.median(a[:, i]):10.2f} {np.percentile(a[:, i], 90):10.2f} {a[:, i].max():10.2f}")
+
+pn = ["gpis_obs_test", "uMP: cull", "uMP: collect+stage (incl obs)", "uMP: serial apply (incl obs)", "evalPoints: serial insert", "train: dirty set", "train: gather", "gpis_leaves_update", "sync_table"]
+print("host profile, ms per frame (calls per frame)")
+for i, n in enumerate(pn):
+    print(f"{n:32s} {secs[i] * 1e3 / nf:9.2f}  ({calls[i] / nf:.1f})")
