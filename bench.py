@@ -302,6 +302,15 @@ def main():
         sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
         fp32_peak = props.multi_processor_count * 128 * 2 * sm_clock / 1e12
         fp32_ach = sq["last_query_flops"] / eval_s / 1e12 if eval_s > 0 else 0.0
+        # DRAM traffic of the evaluation kernels for this exact workload, from the committed ncu capture
+        # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over one step's launches)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("grid") == args.grid and tj.get("frames") == args.frames and world == 1:
+                traffic = float(tj["dram_bytes_per_step"])
+        except (OSError, ValueError, KeyError):
+            traffic = None
         out = {
             "metric": "sdf_grad_var_queries_per_s", "value": total_q / (ms_all * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all,
@@ -313,8 +322,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "kernel": "k_eval_v3<8>/<6>/<4> (+ bucketing)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": comp_bytes,
+                         "traffic": traffic, "kernel": "k_eval_v3<8>/<6>/<4> (+ bucketing)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": comp_bytes, "binding": "fp32_fma (see roofline_fp32)",
+                         "per": "one step = all evaluation launches of one pass over the query grid",
                          "note": "HBM term uses compulsory bytes (44 B/query + each touched leaf record once per pass); "
                                  "the binding roofline of this kernel is FP32 FMA, see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32_fma", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -1015,6 +1016,15 @@ int gpis_debug_timing(long long* out) {   // 64 warps x 32 counters of the instr
     cudaMemcpyFromSymbol(out, g_e3_timing, sizeof(long long) * 64 * 32);
     static long long zeros[64 * 32];
     cudaMemcpyToSymbol(g_e3_timing, zeros, sizeof(zeros));
+    return 0;
+}
+#endif
+
+#ifdef K1_TIMING
+int gpis_debug_train_timing(long long* out) {   // 8 counters of block 0 of k_leaf_train, then reset
+    cudaMemcpyFromSymbol(out, g_k1_timing, sizeof(long long) * 8);
+    static long long zeros[8];
+    cudaMemcpyToSymbol(g_k1_timing, zeros, sizeof(zeros));
     return 0;
 }
 #endif

@@ -15,6 +15,8 @@
 // Bound: FP32 FMA pipe (n^3/3 flops vs ~2n^2 compulsory bytes). No tensor cores: these are
 // independent small factorizations in fp32 with a 1e-4 parity contract.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gpis {
@@ -149,6 +151,13 @@ __device__ __forceinline__ int warp_chol_inv(float* S, float* Dinv, int lane) {
     return bad;
 }
 
+#ifdef K1_TIMING
+__device__ long long g_k1_timing[8];   // clock64 ticks of block 0 per phase: A, B, C, D, E
+#define K1_T(i) { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); g_k1_timing[i] += t_ - k1_t0; k1_t0 = t_; } }
+#else
+#define K1_T(i)
+#endif
+
 __global__ void __launch_bounds__(TRAIN_THREADS, 2)
 k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ samples, TrainParams P,
              int32_t* __restrict__ status) {
@@ -183,6 +192,9 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
+#ifdef K1_TIMING
+    long long k1_t0 = clock64();
+#endif
 
     // ---------------------------------------------------------------- A. samples, gradflag, y
     const float* smp = samples + (size_t)job.sample_off * w9;
@@ -240,12 +252,16 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
     }
     __syncthreads();
     for (int i = tid; i < nb * 32; i += TRAIN_THREADS) zv[i] = yv[i];
+    K1_T(0)
 
     // ---------------------------------------------------------------- B. covariance -> tiles
     // Ordered pairs (a = row sample, b = column sample): an entry (row, col) of the lower triangle
     // is written by exactly one pair, and lanes run along a so the stores are contiguous.
 #define KSTORE(row, col, v) rec_tiles[(size_t)tile_index((row) >> 5, (col) >> 5, nb) * GPIS_TILE_ELEMS + ((col) & 31) * 32 + ((row) & 31)] = (v)
-    {
+    // dimension-specialised (fully unrolled, no local arrays; the 2nd-derivative block is symmetric in its two
+    // axes, covFnc.cpp:205-236, so only DIM(DIM+1)/2 of its entries are evaluated per pair)
+    auto build_cov = [&](auto dimc) {
+        constexpr int DIM = decltype(dimc)::value;
         // N <= 256: the thread block is split into `parts` groups that share the b loop; larger
         // leaves give every thread several rows.
         const int Npad = (N + 31) & ~31;
@@ -261,10 +277,11 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
                 if (b == a0) {
                     KSTORE(a0, a0, (float)(1.0 + (double)sigx[a0]));  // covFnc.cpp:173
                     if (ga >= 0) {
-                        for (int c = 0; c < dim; ++c) {
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) {
                             const int rc = N + c * ng + ga;
                             float v = P.a2 + sigg[a0];  // :182-190 / :355
-                            if (dim == 2 && c == 0) v = (float)((double)P.a2 + sqrt((double)(sigx[a0] * sigg[a0])));  // :352
+                            if (DIM == 2 && c == 0) v = (float)((double)P.a2 + sqrt((double)(sigx[a0] * sigg[a0])));  // :352
                             KSTORE(rc, rc, v);
                         }
                     }
@@ -276,8 +293,9 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
                 const float xb[3] = {pb.x, pb.y, pb.z};
                 // orient differences like the reference: first index = smaller sample index
                 const bool fwd = a0 < b;
-                float d[3], s2 = 0.f;
-                for (int c = 0; c < dim; ++c) {
+                float d[DIM], s2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
                     d[c] = fwd ? (xa[c] - xb[c]) : (xb[c] - xa[c]);
                     s2 = (c == 0) ? d[c] * d[c] : s2 + d[c] * d[c];
                 }
@@ -287,17 +305,23 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
                 if (a0 > b) KSTORE(a0, b, kf_val(r, P.a, e));
                 if (ga >= 0) {
                     // d/dc at a  vs  value at b:  -kf1(x_a - x_b)   (covFnc.cpp:198-203 / 239-249)
-                    for (int c = 0; c < dim; ++c) {
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) {
                         const float k1 = kf1_val(d[c], P.a, e);   // kf1(x_first - x_second)
                         KSTORE(N + c * ng + ga, b, fwd ? -k1 : k1);
                     }
                     if (gb >= 0) {
-                        for (int c = 0; c < dim; ++c)
-                            for (int e2 = 0; e2 < dim; ++e2) {
+                        float k2[DIM][DIM];
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c)
+#pragma unroll
+                            for (int e2 = c; e2 < DIM; ++e2) k2[c][e2] = k2[e2][c] = kf2_val(r, d[c], d[e2], c == e2 ? 1.f : 0.f, P.a, e);
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c)
+#pragma unroll
+                            for (int e2 = 0; e2 < DIM; ++e2) {
                                 const int row = N + c * ng + ga, col = N + e2 * ng + gb;
-                                if (row <= col) continue;
-                                const int c0 = min(c, e2), e0 = max(c, e2);
-                                KSTORE(row, col, kf2_val(r, d[c0], d[e0], c == e2 ? 1.f : 0.f, P.a, e));
+                                if (row > col) KSTORE(row, col, k2[c][e2]);
                             }
                     }
                 }
@@ -305,11 +329,14 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         }
         // identity on the padded diagonal
         for (int i = n + tid; i < nb * 32; i += TRAIN_THREADS) KSTORE(i, i, 1.0f);
-    }
+    };
+    if (dim == 3) build_cov(std::integral_constant<int, 3>{});
+    else build_cov(std::integral_constant<int, 2>{});
 #undef KSTORE
     __threadfence_block();
     fence_proxy_async();
     __syncthreads();
+    K1_T(1)
 
     // ---------------------------------------------------------------- C. blocked Cholesky + forward solve
     int bad_total = 0;
@@ -400,6 +427,7 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         }
     }
 
+    K1_T(2)
     // ---------------------------------------------------------------- D. backward solve L^T alpha = z
     // alpha_j = inv(Ljj)^T ( z_j - sum_{i>j} L(i,j)^T alpha_i ), j = nb-1 .. 0. zv holds z; it is
     // overwritten by alpha block by block. Warps split i; lane = column k of the tile.
@@ -434,6 +462,7 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
     }
     for (int i = tid; i < nb * 32; i += TRAIN_THREADS) rec_alpha[i] = (i < n) ? zv[i] : 0.f;
 
+    K1_T(3)
     // ---------------------------------------------------------------- E. query form of the factor
     // Off-diagonal tiles are rewritten in place as G(i,j) = L(i,j) inv(Ljj): the query's block
     // elimination then needs no per-block triangular solve on its dependency chain (query_v2.cuh).
@@ -463,6 +492,7 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         __syncthreads();
     }
 
+    K1_T(4)
     if (tid == 0) {
         LeafHeader* h = reinterpret_cast<LeafHeader*>(rec);
         h->N = N; h->ng = ng; h->n = n; h->nb = nb; h->dim = dim; h->chol_fail = bad_total; h->slot = job.slot;

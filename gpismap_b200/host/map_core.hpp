@@ -12,6 +12,7 @@
 #include <map>
 #include <set>
 #include <unordered_set>
+#include <thread>
 #include <vector>
 
 #include "gpis_b200.h"
@@ -134,28 +135,56 @@ public:
         }
         active.clear();                                           // GPisMap3.cpp:789
         g_prof_s[5] += now_s() - tp0; g_prof_n[5] += 1; tp0 = now_s();
+        // Training sets (QueryRange per dirty leaf, GPisMap3.cpp:705-709) are independent read-only tree
+        // queries: gathered by a few host threads into per-chunk buffers, concatenated in leaf order.
+        constexpr int W = 2 * D + 3;
+        std::vector<int> cids;
+        for (int cid : update_set)
+            if (!tree->is_empty_leaf(cid)) cids.push_back(cid);   // an empty leaf is never a query candidate; its GP is unobservable
+        struct Part { std::vector<int32_t> cells, counts; std::vector<float> centres, samples; };
+        const int nthr = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, (int)cids.size() / 16 + 1}));
+        std::vector<Part> parts(nthr);
+        auto gather = [&](int t) {
+            Part& P = parts[t];
+            const size_t b = cids.size() * t / nthr, e = cids.size() * (t + 1) / nthr;
+            std::vector<int> ids;
+            for (size_t i = b; i < e; ++i) {
+                const int cid = cids[i];
+                const auto& n = tree->cell(cid);
+                ids.clear();
+                tree->query_range(n.c, n.half * rtimes_, ids);        // GPisMap3.cpp:705-709
+                if (ids.empty()) continue;                             // GPisMap3.cpp:710
+                int32_t cc[3];
+                cell_of(cid, cc);
+                for (int a = 0; a < D; ++a) { P.cells.push_back(cc[a]); P.centres.push_back(n.c[a]); }
+                for (int s : ids) {
+                    const Sample<D>& sm = tree->sample(s);
+                    for (int a = 0; a < D; ++a) P.samples.push_back(sm.pos[a]);
+                    for (int a = 0; a < D; ++a) P.samples.push_back(sm.grad[a]);
+                    P.samples.push_back(sm.val); P.samples.push_back(sm.pose_sig); P.samples.push_back(sm.grad_sig);
+                }
+                P.counts.push_back((int32_t)ids.size());
+            }
+        };
+        if (nthr == 1) gather(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nthr; ++t) th.emplace_back(gather, t);
+            gather(0);
+            for (auto& x : th) x.join();
+        }
         std::vector<int32_t> cells;
         std::vector<float> centres;
         std::vector<int32_t> offsets(1, 0);
         std::vector<float> samples;
-        std::vector<int> ids;
-        constexpr int W = 2 * D + 3;
-        for (int cid : update_set) {
-            if (tree->is_empty_leaf(cid)) continue;   // an empty leaf is never a query candidate; its GP is unobservable
-            const auto& n = tree->cell(cid);
-            ids.clear();
-            tree->query_range(n.c, n.half * rtimes_, ids);        // GPisMap3.cpp:705-709
-            if (ids.empty()) continue;                             // GPisMap3.cpp:710
-            int32_t cc[3];
-            cell_of(cid, cc);
-            for (int a = 0; a < D; ++a) { cells.push_back(cc[a]); centres.push_back(n.c[a]); }
-            for (int s : ids) {
-                const Sample<D>& sm = tree->sample(s);
-                for (int a = 0; a < D; ++a) samples.push_back(sm.pos[a]);
-                for (int a = 0; a < D; ++a) samples.push_back(sm.grad[a]);
-                samples.push_back(sm.val); samples.push_back(sm.pose_sig); samples.push_back(sm.grad_sig);
-            }
-            offsets.push_back((int32_t)(samples.size() / W));
+        for (const Part& P : parts) {
+            cells.insert(cells.end(), P.cells.begin(), P.cells.end());
+            centres.insert(centres.end(), P.centres.begin(), P.centres.end());
+            samples.insert(samples.end(), P.samples.begin(), P.samples.end());
+            for (int32_t c : P.counts) offsets.push_back(offsets.back() + c);
+        }
+        for (size_t i = 0; i + D <= cells.size(); i += D) {
+            int32_t cc[3] = {cells[i], cells[i + 1], D == 3 ? cells[i + 2] : 0};
             device_cells[pack(cc)] = {cc[0], cc[1], cc[2]};
         }
         const int nl = (int)offsets.size() - 1;
