@@ -385,7 +385,30 @@ def cpu_baseline(args, gmap, X):
         M.test(q[:nq], res)
         dt = time.perf_counter() - t0
         ev = int((res[:, 4] < 1.0).sum())
-        return {"value": nq / dt, "unit": "queries/s", "cores": cores, "kind": "reference",
+        # the same points through the GPU map (built from the same samples): a parity report at bench-scale leaf
+        # sizes, on the points whose whole candidate neighbourhood lies inside the sub-box the reference trained
+        parity = None
+        try:
+            from gpismap_b200 import hostapi
+            g2 = hostapi.GPisMap3()            # same samples, same insertion order, every leaf trained on the final set
+            g2.insert_samples(S[sel])
+            g2.train_active()
+            got = g2.test(np.ascontiguousarray(q[:nq]))
+            g2.close()
+            inner = np.all((q[:nq] > lo + 0.05) & (q[:nq] < hi - 0.05), axis=1) & (res[:, 4] < 1.0) & (got[:, 4] < 1.0)
+            a, b = got[inner].astype(np.float64), res[inner].astype(np.float64)
+            ef = np.abs(a[:, 0] - b[:, 0]) / np.maximum(np.abs(b[:, 0]), 0.05)
+            eg = np.linalg.norm(a[:, 1:4] - b[:, 1:4], axis=1) / np.maximum(np.linalg.norm(b[:, 1:4], axis=1), 0.1)
+            evr = (np.abs(a[:, 4:] - b[:, 4:]) / np.maximum(np.abs(b[:, 4:]), 1e-3)).max(1)
+            parity = {"rows": int(inner.sum()),
+                      "f_rel": {"median": float(np.median(ef)), "p99": float(np.percentile(ef, 99)), "within_1e-4": float((ef < 1e-4).mean())},
+                      "grad_rel": {"median": float(np.median(eg)), "p99": float(np.percentile(eg, 99)), "within_1e-4": float((eg < 1e-4).mean())},
+                      "var_rel": {"median": float(np.median(evr)), "p99": float(np.percentile(evr, 99)), "within_1e-3": float((evr < 1e-3).mean())},
+                      "note": "a second GPU map loaded with the same samples in the same order (insertSamples + trainActive) vs the reference's own train+test; floors 0.05 (f), 0.1 (|grad|), 1e-3 (var) as in tests/helpers.py; "
+                              "rows the fp32 reference itself does not pin (tests/helpers.py::check_rows) are included"}
+        except Exception as e:
+            parity = {"error": repr(e)}
+        return {"value": nq / dt, "unit": "queries/s", "cores": cores, "kind": "reference", "parity_vs_reference": parity,
                 "sample": f"{nq} grid points of the sub-box {np.round(lo,2).tolist()}..{np.round(hi,2).tolist()} ({ev} evaluated) against "
                           f"{ntrain} leaves trained by the reference's updateGPs from the same samples ({t_train:.1f} s); {dt:.1f} s of GPisMap3::test",
                 "leaf_train_s": t_train, "leaves_trained": ntrain}
