@@ -164,6 +164,23 @@ private:
         for (int a = 0; a < D; ++a) if (hi[a] < n.lo[a] || lo[a] > n.hi[a]) return false;
         return true;
     }
+    // The one child whose box can contain p, when that is certain. The reference tries the children in visiting
+    // order and each child tests its own float box (c +- l computed in float, so neighbouring boxes can overlap or
+    // leave a gap of an ulp around the parent's centre planes). Away from those planes — by more than a few ulps
+    // of |c| + half — every other child rejects p on its first comparison and has no side effect, so descending
+    // into this child alone is the same computation; near a plane the callers fall back to the full scan.
+    int certain_child(const Cell& n, const float* p) const {
+        int k = 0;
+        for (int a = 0; a < D; ++a) {
+            const float d = p[a] - n.c[a];
+            const float tol = 9.6e-7f * (std::fabs(n.c[a]) + n.half);   // 8 ulp
+            if (!(std::fabs(d) > tol)) return -1;
+            const bool up = d > 0.f;
+            if (a == 0) { if (up) k |= 1; }
+            else if (!up) k |= (1 << a);
+        }
+        return k;
+    }
     // Subdivide (octree.cpp:672-713): children at c +- half/2, visiting order as above
     void subdivide(int id, int except_k = -1, int except_cell = -1) {
         const int b = alloc_children();
@@ -280,12 +297,18 @@ private:
                 if (sqdist(samples_[cells_[id].sample].pos, p) < P.min_half_sqr) return false;
                 const int old = cells_[id].sample;
                 subdivide(id);
-                for (int k = 0; k < NCH; ++k)
-                    if (insert_rec(cells_[id].child0 + k, old, quads)) break;
+                {
+                    const int ck = certain_child(cells_[id], samples_[old].pos);
+                    if (ck >= 0) insert_rec(cells_[id].child0 + ck, old, quads);
+                    else
+                        for (int k = 0; k < NCH; ++k)
+                            if (insert_rec(cells_[id].child0 + k, old, quads)) break;
+                }
                 cells_[id].sample = -1;   // dropped silently if no child took it (lattice-plane rejection)
             }
         }
-        for (int k = 0; k < NCH; ++k) {
+        const int ck = certain_child(cells_[id], p);
+        for (int k = (ck >= 0 ? ck : 0); k < (ck >= 0 ? ck + 1 : NCH); ++k) {
             if (insert_rec(cells_[id].child0 + k, s, quads)) {
                 if (quads && reg_ok(cells_[id])) quads->push_back(id);
                 update_count(id);
@@ -301,6 +324,8 @@ private:
         if (n.child0 < 0 && n.sample < 0) return false;
         if (n.sample >= 0 && sqdist(samples_[n.sample].pos, p) < P.min_half_sqr) return true;
         if (n.child0 < 0) return false;
+        const int ck = certain_child(n, p);
+        if (ck >= 0) return is_not_new(n.child0 + ck, p);
         for (int k = 0; k < NCH; ++k) if (is_not_new(n.child0 + k, p)) return true;
         return false;
     }
@@ -314,7 +339,8 @@ private:
         }
         if (cells_[id].child0 < 0) return false;
         bool res = false;
-        for (int k = 0; k < NCH; ++k) {
+        const int ck = certain_child(cells_[id], p);
+        for (int k = (ck >= 0 ? ck : 0); k < (ck >= 0 ? ck + 1 : NCH); ++k) {
             if (short_circuit && res) break;
             res = remove_rec(cells_[id].child0 + k, p, short_circuit, freed) || res;
         }
