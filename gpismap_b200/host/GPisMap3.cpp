@@ -85,6 +85,9 @@ struct GPisMap3::Impl {
     };
     void reeval_stage1(const std::vector<int>& ids, std::vector<ReEval>& st);
     void reeval_stage2(std::vector<ReEval>& st, std::vector<float>& rinv0, std::vector<float>& var);
+    struct ReOut { int action; float pos_new[3], grad_new[3], noise, grad_noise; };   // 0 nothing, 1 double the sigmas, 2 replace
+    ReOut reeval_compute(const ReEval& e, const float* rinv0, const float* var) const;
+    void reeval_commit(const ReEval& e, const ReOut& o);
     void reeval_apply(const ReEval& e, const float* rinv0, const float* var);
 };
 
@@ -238,8 +241,13 @@ void GPisMap3::Impl::reeval_stage2(std::vector<ReEval>& st, std::vector<float>& 
     obs_test(vu, rinv0, var);
 }
 
-// The rest of one reEvalPoints iteration (GPisMap3.cpp:413-567) for one sample.
-void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const float* var) {
+// The rest of one reEvalPoints iteration (GPisMap3.cpp:413-567) for one sample, in two halves: the numerics
+// (a pure function of the observation tests, the pose and the sample's own fields, which nobody else touches
+// before its commit) and the tree mutation. updateMapPoints runs the first half for all in-view samples on a
+// few host threads and the second half serially in the reference's order.
+GPisMap3::Impl::ReOut GPisMap3::Impl::reeval_compute(const ReEval& e, const float* rinv0, const float* var) const {
+    ReOut out{};
+    out.action = 0;
     static const float Zp[6] = {0.0f, 0.0f, 0.0f, 0.0f, 1.0f, -1.0f};
     auto* tree = core.tree;
     const float w = (float)(1.0 / 6.0);
@@ -258,9 +266,9 @@ void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const flo
         r0_sqr_sum += r0 * r0;
         r0_mean += w * r0;
     }
-    if (last_var > setting.obs_var_thre) return;
+    if (last_var > setting.obs_var_thre) return out;
 
-    Sample<3>& old = tree->sample(e.sample);
+    const Sample<3>& old = tree->sample(e.sample);
     const float pos[3] = {old.pos[0], old.pos[1], old.pos[2]};
     const float grad[3] = {old.grad[0], old.grad[1], old.grad[2]};
     float gnl[3];
@@ -268,10 +276,9 @@ void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const flo
     gnl[1] = (occ[2] - occ[3]) / setting.delx;
     gnl[2] = (occ[4] - occ[5]) / setting.delx;
     const float norm_grad_new = std::sqrt(gnl[0] * gnl[0] + gnl[1] * gnl[1] + gnl[2] * gnl[2]);
-    if ((double)norm_grad_new < 1e-3) {   // uncertainty increased (GPisMap3.cpp:451-454)
-        old.pose_sig = (float)(2.0 * (double)old.pose_sig);
-        old.grad_sig = (float)(2.0 * (double)old.grad_sig);
-        return;
+    if ((double)norm_grad_new < 1e-3) {   // uncertainty increased (GPisMap3.cpp:451-454): applied at commit
+        out.action = 1;
+        return out;
     }
     float r_var = (float)((double)r0_sqr_sum / 5.0 - (double)(r0_mean * r0_mean) * 6.0 / 5.0);
     r_var /= setting.delx;
@@ -330,6 +337,24 @@ void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const flo
         grad_noise = std::min((float)1.0, std::max(grad_noise * grad_noise_old / grad_noise_sum + dist2, setting.map_noise_param));
         noise = std::max((noise * noise_old / pos_noise_sum + dist2), setting.map_noise_param);
     }
+    out.action = 2;
+    for (int a = 0; a < 3; ++a) { out.pos_new[a] = pos_new[a]; out.grad_new[a] = grad_new[a]; }
+    out.noise = noise; out.grad_noise = grad_noise;
+    return out;
+}
+
+void GPisMap3::Impl::reeval_commit(const ReEval& e, const ReOut& o) {
+    auto* tree = core.tree;
+    if (o.action == 0) return;
+    if (o.action == 1) {
+        Sample<3>& old = tree->sample(e.sample);
+        old.pose_sig = (float)(2.0 * (double)old.pose_sig);
+        old.grad_sig = (float)(2.0 * (double)old.grad_sig);
+        return;
+    }
+    const float noise = o.noise, grad_noise = o.grad_noise;
+    const float* pos_new = o.pos_new;
+    const float* grad_new = o.grad_new;
     // remove the old sample (GPisMap3.cpp:536), then try the fused one
     std::vector<int> freed;
     tree->remove_tracked(e.sample, freed);
@@ -342,6 +367,10 @@ void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const flo
     sm.val = -setting.fbias; sm.pose_sig = noise; sm.grad_sig = grad_noise;
     sm.grad[0] = grad_new[0]; sm.grad[1] = grad_new[1]; sm.grad[2] = grad_new[2];
     core.activate(touched);
+}
+
+void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const float* var) {
+    reeval_commit(e, reeval_compute(e, rinv0, var));
 }
 
 // ------------------------------------------------------------------ updateMapPoints (GPisMap3.cpp:258-319)
@@ -397,6 +426,20 @@ void GPisMap3::Impl::updateMapPoints() {
     }
     g_prof_s[2] += now_s() - tp0; g_prof_n[2] += 1;
     ProfScope ps3(3);
+    // numerics of every pre-existing in-view sample, in parallel (see reeval_compute)
+    std::vector<ReOut> pre_out(st.size());
+    {
+        const int nthr = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, (int)st.size() / 2048 + 1}));
+        auto work = [&](int t) {
+            const size_t b = st.size() * t / nthr, e2 = st.size() * (t + 1) / nthr;
+            for (size_t i = b; i < e2; ++i)
+                if (st[i].alive1) pre_out[i] = reeval_compute(st[i], &rinv0[pre_probe[i]], &var[pre_probe[i]]);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
     // Serial pass in the reference's order. Samples created during this pass (a fused point that
     // landed in a leaf not yet visited) are evaluated on demand, leaf by leaf.
     std::vector<int> ids, fresh;
@@ -414,7 +457,7 @@ void GPisMap3::Impl::updateMapPoints() {
         for (int s : ids) {
             if (s < (int)pre_index.size() && pre_index[s] >= 0) {
                 const int i = pre_index[s];
-                if (st[i].alive1) reeval_apply(st[i], &rinv0[pre_probe[i]], &var[pre_probe[i]]);
+                if (st[i].alive1) reeval_commit(st[i], pre_out[i]);
             } else {
                 const ReEval& e = st2[fi++];
                 if (e.alive1) { reeval_apply(e, &rinv0b[fprobe], &varb[fprobe]); fprobe += 6; }
@@ -455,6 +498,63 @@ void GPisMap3::Impl::evalPoints() {
     std::vector<float> rinv0p, varp;
     obs_test(vup, rinv0p, varp);
 
+    // numerics of every measurement that passed batch 1 (occupancy probes, normal, noise terms: a pure function
+    // of the observation tests and the pose), on a few host threads; the serial loop below only touches the tree
+    struct NewOut { bool failed; float grad[3], noise, grad_noise; };
+    std::vector<NewOut> pre(K);
+    {
+        auto compute = [&](int k) {
+            NewOut o{};
+            const int k3 = 3 * k;
+            float occ[6] = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+            float occ_mean = 0.0f;
+            const float* r0 = &rinv0p[probe_of[k]];
+            const float* vr = &varp[probe_of[k]];
+            o.failed = false;
+            for (int i = 0; i < 6; i++) {
+                if (vr[i] > setting.obs_var_thre) { o.failed = true; break; }
+                const float Z = obs_valid_xyzlocal[k3 + 2] + setting.delx * Zp[i];
+                occ[i] = occ_test((float)(1.0 / (double)Z), r0[i], (float)((double)Z * 30.0));
+                occ_mean += w * occ[i];
+            }
+            if (o.failed) return o;   // GPisMap3.cpp:652-655
+            float noise = 100.0f, grad_noise = 1.00f;
+            float grad[3];
+            grad[0] = (occ[0] - occ[1]) / setting.delx;
+            grad[1] = (occ[2] - occ[3]) / setting.delx;
+            grad[2] = (occ[4] - occ[5]) / setting.delx;
+            float norm_grad = grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2];
+            if ((double)norm_grad > 1e-6) {
+                norm_grad = std::sqrt(norm_grad);
+                const float glx = grad[0] / norm_grad, gly = grad[1] / norm_grad, glz = grad[2] / norm_grad;
+                grad[0] = pose_R[0] * glx + pose_R[3] * gly + pose_R[6] * glz;
+                grad[1] = pose_R[1] * glx + pose_R[4] * gly + pose_R[7] * glz;
+                grad[2] = pose_R[2] * glx + pose_R[5] * gly + pose_R[8] * glz;
+                const float* xl = &obs_valid_xyzlocal[k3];
+                const float dist = std::sqrt(xl[0] * xl[0] + xl[1] * xl[1] + xl[2] * xl[2]);
+                noise = setting.min_position_noise * (saturate(dist, 1.0f, noise));
+                grad_noise = saturate(std::fabs(occ_mean), setting.min_grad_noise, grad_noise);
+                const float view_ang = std::max(-(xl[0] * glx + xl[1] * gly + xl[2] * glz) / dist, (float)1e-1);
+                const float view_ang2 = view_ang * view_ang;
+                const float view_noise = (float)((double)setting.min_position_noise * ((1.0 - (double)view_ang2) / (double)view_ang2));
+                noise += view_noise;
+            }
+            o.grad[0] = grad[0]; o.grad[1] = grad[1]; o.grad[2] = grad[2];
+            o.noise = noise; o.grad_noise = grad_noise;
+            return o;
+        };
+        const int nthr = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, K / 4096 + 1}));
+        auto work = [&](int t) {
+            const int b = (int)((int64_t)K * t / nthr), e = (int)((int64_t)K * (t + 1) / nthr);
+            for (int k = b; k < e; ++k)
+                if (!(varc[k] > setting.obs_var_thre)) pre[k] = compute(k);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+
     std::vector<int> touched, freed;
     ProfScope ps4(4);
     for (int k = 0; k < K; k++) {
@@ -462,47 +562,16 @@ void GPisMap3::Impl::evalPoints() {
         if (varc[k] > setting.obs_var_thre) continue;
         const int s = core.try_insert(&obs_valid_xyzglobal[k3], touched);
         if (s < 0) continue;
-        float occ[6] = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
-        float occ_mean = 0.0f;
-        const float* r0 = &rinv0p[probe_of[k]];
-        const float* vr = &varp[probe_of[k]];
-        bool failed = false;
-        for (int i = 0; i < 6; i++) {
-            if (vr[i] > setting.obs_var_thre) { failed = true; break; }
-            const float Z = obs_valid_xyzlocal[k3 + 2] + setting.delx * Zp[i];
-            occ[i] = occ_test((float)(1.0 / (double)Z), r0[i], (float)((double)Z * 30.0));
-            occ_mean += w * occ[i];
-        }
-        if (failed) {   // GPisMap3.cpp:652-655
+        const NewOut& o = pre[k];
+        if (o.failed) {   // GPisMap3.cpp:652-655
             freed.clear();
             tree->remove_plain(s, freed);
             core.drop_freed(freed);
             continue;
         }
-        float noise = 100.0f, grad_noise = 1.00f;
-        float grad[3];
-        grad[0] = (occ[0] - occ[1]) / setting.delx;
-        grad[1] = (occ[2] - occ[3]) / setting.delx;
-        grad[2] = (occ[4] - occ[5]) / setting.delx;
-        float norm_grad = grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2];
-        if ((double)norm_grad > 1e-6) {
-            norm_grad = std::sqrt(norm_grad);
-            const float glx = grad[0] / norm_grad, gly = grad[1] / norm_grad, glz = grad[2] / norm_grad;
-            grad[0] = pose_R[0] * glx + pose_R[3] * gly + pose_R[6] * glz;
-            grad[1] = pose_R[1] * glx + pose_R[4] * gly + pose_R[7] * glz;
-            grad[2] = pose_R[2] * glx + pose_R[5] * gly + pose_R[8] * glz;
-            const float* xl = &obs_valid_xyzlocal[k3];
-            const float dist = std::sqrt(xl[0] * xl[0] + xl[1] * xl[1] + xl[2] * xl[2]);
-            noise = setting.min_position_noise * (saturate(dist, 1.0f, noise));
-            grad_noise = saturate(std::fabs(occ_mean), setting.min_grad_noise, grad_noise);
-            const float view_ang = std::max(-(xl[0] * glx + xl[1] * gly + xl[2] * glz) / dist, (float)1e-1);
-            const float view_ang2 = view_ang * view_ang;
-            const float view_noise = (float)((double)setting.min_position_noise * ((1.0 - (double)view_ang2) / (double)view_ang2));
-            noise += view_noise;
-        }
         Sample<3>& sm = tree->sample(s);
-        sm.val = -setting.fbias; sm.pose_sig = noise; sm.grad_sig = grad_noise;
-        sm.grad[0] = grad[0]; sm.grad[1] = grad[1]; sm.grad[2] = grad[2];
+        sm.val = -setting.fbias; sm.pose_sig = o.noise; sm.grad_sig = o.grad_noise;
+        sm.grad[0] = o.grad[0]; sm.grad[1] = o.grad[1]; sm.grad[2] = o.grad[2];
         core.activate(touched);
     }
 }
