@@ -1029,6 +1029,21 @@ int gpis_debug_train_timing(long long* out) {   // 8 counters of block 0 of k_le
 }
 #endif
 
+// Development/test aid (no device needed): the elimination program of k_eval_v3 for (nb, warp) as int32 words
+// (query_v3.cuh: header, waves, visits, terminators, variance rows). Returns the number of words, or the
+// required count when cap is too small.
+int gpis_debug_program(int nb, int warp, int32_t* out, int cap) {
+    if (nb < 1 || nb > E3_PROG_MAXNB || warp < 0 || warp >= E3_WARPS) return -1;
+    E3WarpProg wp[E3_WARPS];
+    for (int w = 0; w < E3_WARPS; ++w) e3_build_warp(nb, w, wp[w]);
+    e3_assign_variance(nb, wp);
+    std::vector<int4> recs;
+    e3_emit_program(wp[warp], recs);
+    const int words = (int)recs.size() * 4;
+    if (out && cap >= words) std::memcpy(out, recs.data(), sizeof(int4) * recs.size());
+    return words;
+}
+
 int gpis_set_eval_version(gpis_ctx* ctx, int v) {
     if (!ctx || v < 1 || v > 3) return GPIS_ERR_ARG;
     ctx->eval_version = v;

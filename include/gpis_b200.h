@@ -181,6 +181,16 @@ typedef struct gpis_stats {
 } gpis_stats;
 int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out);
 
+/* ---- development and test aids (not part of the drop-in surface) ------------------------------
+ * gpis_set_eval_version: 3 = production evaluation kernel (k_eval_v3, default), 2 = first grouped
+ *   kernel, 1 = one CTA per (query, leaf) pair; the parity tests run all three.
+ * gpis_debug_program: the host-generated visit program of k_eval_v3 for a leaf of nb block rows and
+ *   one warp, as int32 words (layout: gpismap_b200/csrc/query_v3.cuh); needs no device. Returns the
+ *   word count (also when cap is too small), -1 on bad arguments. tests/test_eval_programs.py checks
+ *   coverage, the publish protocol and deadlock freedom on these programs. */
+int gpis_set_eval_version(gpis_ctx* ctx, int version);
+int gpis_debug_program(int nb, int warp, int32_t* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,5 +196,6 @@ int gpis_get_stats(gpis_ctx* c, gpis_stats* out) {
     return GPIS_OK;
 }
 int gpis_set_eval_version(gpis_ctx*, int) { return GPIS_OK; }
+int gpis_debug_program(int, int, int32_t*, int) { return -1; }
 
 }  // extern "C"
