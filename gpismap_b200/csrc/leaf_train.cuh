@@ -49,7 +49,7 @@ struct TrainSmem {
     static constexpr int off_stage = 0;                                               // 2 stages
     static constexpr int off_scratch = 0;   // per-warp 4 KB scratch aliases stage 0 (idle outside the bk loop)
     static constexpr int off_dinv = 2 * stage_bytes;                                  // 4 KB
-    static constexpr int off_bar = off_dinv + GPIS_TILE_BYTES;                        // 2 mbarriers
+    static constexpr int off_bar = off_dinv + GPIS_TILE_BYTES;                        // 4 mbarriers (full/empty per stage)
     static constexpr int off_misc = off_bar + 64;                                     // small arrays
     // misc: pts float4[N] | sigx[N] | sigg[N] | y[nbmax*32] | z(=t) [nbmax*32] | wtot[32]
     static int total(int Nmax, int nbmax) {
@@ -188,8 +188,10 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
     const int ntiles = nb * (nb + 1) / 2;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
+        mbar_init(&bars[0], 1);             // full[0], full[1]: TMA completion
         mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], TRAIN_WARPS);   // empty[0], empty[1]: every warp is done reading the stage
+        mbar_init(&bars[3], TRAIN_WARPS);
         fence_mbar_init();
     }
 #ifdef K1_TIMING
@@ -340,7 +342,8 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
 
     // ---------------------------------------------------------------- C. blocked Cholesky + forward solve
     int bad_total = 0;
-    uint32_t phase_bits = 0;  // parity of each stage barrier
+    uint32_t phase_bits = 0;  // parity of each stage's full barrier
+    uint32_t fills[2] = {0u, 0u};   // thread 0: refills issued per stage (phase count of its empty barrier)
     for (int bj = 0; bj < nb; ++bj) {
         const int ncol = nb - bj;  // tiles bi = bj .. nb-1
         for (int g0 = 0; g0 < ncol; g0 += TRAIN_WARPS) {
@@ -354,9 +357,13 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
             const bool rider = (g0 == 0 && warp == 0);
             if (rider) tz = zv[bj * 32 + lane];
 
-            // pipeline over bk: stage s holds A tiles (bi, bk) for this group + B tile (bj, bk)
+            // pipeline over bk: stage s holds A tiles (bi, bk) for this group + B tile (bj, bk). Producer/consumer
+            // protocol: the warps never wait for each other, only thread 0 waits (on empty[s]) before it refills
+            // a stage; the first two fills of a group follow a block barrier and need no wait.
             auto issue = [&](int bk, int s) {
                 if (tid == 0) {
+                    if (bk >= 2) mbar_wait(&bars[2 + s], (fills[s] - 1u) & 1u);
+                    ++fills[s];
                     mbar_expect_tx(&bars[s], (uint32_t)(gcount + 1) * GPIS_TILE_BYTES);
                     // A tiles of the group are consecutive in the column-block-major array
                     tma_load_1d(stage[s], rec_tiles + (size_t)tile_index(bj + g0, bk, nb) * GPIS_TILE_ELEMS,
@@ -379,7 +386,8 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
                     for (int k = 0; k < 32; ++k) sdot = fmaf(B[k * 32 + lane], zv[bk * 32 + k], sdot);
                     tz -= sdot;
                 }
-                __syncthreads();  // everyone is done with stage s before it is refilled
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[2 + s]);   // this warp is done with stage s
             }
 
             if (g0 == 0) {
