@@ -308,3 +308,26 @@ def test_bench_scale_map_matches_reference(cabi):
     assert p["f_rel"]["within_1e-4"] >= 0.999 and p["f_rel"]["p99"] < 1e-4, p
     assert p["var_rel"]["within_1e-3"] >= 0.999 and p["var_rel"]["p99"] < 1e-3, p
     assert p["grad_rel"]["within_1e-4"] >= 0.85 and p["grad_rel"]["p99"] < 1e-3 and p["grad_rel"]["median"] < 5e-5, p
+
+
+def test_query_on_sample_position_nan_pattern(cabi, oracle):
+    """r = 0 makes kf2 divide by zero in the reference (covFnc.cpp:29-33): a query placed exactly on a sample with
+    a usable normal gets NaN gradients and gradient variances there, finite f and var_f. The CUDA path must
+    reproduce the same pattern, and agree on the finite entries."""
+    rng = np.random.default_rng(2)
+    P = H.P3
+    ctx = cabi.Ctx(3)
+    cells = np.array([[6, -3, 1]], np.int32)
+    centres = ((2 * cells + 1) * np.float64(np.float32(P["half"]))).astype(np.float32)
+    s = H.leaf_samples3(60, rng, spread=0.03)
+    s[:, :3] += centres[0] - np.array([0.3125, -0.1375, 0.0625], np.float32)
+    assert (ctx.leaves_update(cells, centres, [0, len(s)], s) == 0).all()
+    x = np.concatenate([s[:12, :3], s[12:16, :3] + np.float32(1e-3)]).astype(np.float32)
+    got = ctx.query(x)
+    gp = oracle.gp_train(3, s, P["scale"], P["noise"])
+    want = oracle.make_map(3, centres, P["half"], [gp], P["search"], P["var_thre"], P["noise"]).test(x)
+    assert np.isnan(want).any() and not np.isnan(want[:, 0]).any()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    fin = ~np.isnan(want)
+    assert np.allclose(got[fin], want[fin], rtol=2e-3, atol=1e-5)
+    ctx.close()
