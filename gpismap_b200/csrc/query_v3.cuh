@@ -7,13 +7,18 @@
 // which is L^{-1} k* (OnGPIS.cpp:199-213) evaluated block-wise.
 //
 // Mapping (B200): 8 warps per CTA, one CTA per SM. U (npad x 4*QBT floats) stays in shared memory.
-// Block rows are dealt to warps modulo 8 and processed in waves of 32 block rows: inside a wave a
-// warp keeps its (up to) 4 block rows as a 16x8-per-lane register accumulator, so one k-step costs
-// 24 shared-memory words per lane for 128 FMAs — the FMA pipe, not the shared-memory pipe, is the
-// limiter (a 4x8 lane tile was measured smem-bound: profiles/r01). G tiles stream L2 -> shared memory as
-// 1 KB quarter-tiles through per-warp double-buffered TMA bulk copies (mbarrier completion), issued one
-// step ahead and running across column and wave boundaries (G is read-only). A row's tile of U is written
-// to shared memory exactly once, when it becomes final. One __syncthreads per block column.
+// Block rows are dealt to the warps in snake order and processed in waves of 32 block rows (the partial wave
+// first): inside a wave a warp keeps its (up to) 4 block rows as a 16x8-per-lane register accumulator, so one
+// k-step costs 24 shared-memory words per lane for 128 FMAs (packed FFMA2, operands software-pipelined:
+// mma_tile.cuh; a 4x8 lane tile was measured smem-bound, profiles/r01_history.md). G tiles stream L2 -> shared
+// memory as 1 KB quarter tiles through per-warp double-buffered cp.async copies issued one step ahead (running
+// across column and wave boundaries: G is read-only); 1 KB TMA bulk copies are kept behind -DE3_USE_TMA (12 %
+// slower here). Synchronisation is dataflow: one mbarrier per block row, armed when the row's tile of U is final
+// and written to shared memory (exactly once); the owner of row j+1 applies column j to that row first and
+// publishes it before touching its other rows (lookahead). There is no block-wide barrier inside the elimination.
+// The order of visits is not computed on the device: the host generates, per (nb, warp), a program of 32-byte
+// records (e3_build_warp) and a list of the rows whose variance product the warp computes (e3_assign_variance);
+// tests/test_eval_programs.py checks coverage, publish protocol and deadlock freedom of those programs on the CPU.
 #pragma once
 #include <algorithm>
 #include <string>
