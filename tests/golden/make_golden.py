@@ -92,6 +92,32 @@ def seq2d():
     return out
 
 
+def seq2d_demo():
+    """The whole 2-D demo run (matlab/demo_gpisMap.m:26-40: frames 101:100:2801 of data/2D/gazebo1.mat, test grid
+    0.1 m over [-5,20]x[-15,5]): inputs for BASELINE configs[0], and the reference's leaves after every scan plus
+    its result rows on every 7th grid point after the last one."""
+    import scipy.io
+    m = scipy.io.loadmat("/root/reference/data/2D/gazebo1.mat")
+    thetas = m["thetas"].ravel().astype(np.float32)
+    frames = list(range(100, m["poses"].shape[0], 100))       # 0-based 100, 200, ..., 2800
+    ranges = m["ranges"][frames].astype(np.float32)
+    poses = m["poses"][frames]
+    pose6 = np.stack([[x, y, np.cos(p), np.sin(p), -np.sin(p), np.cos(p)] for x, y, p in poses]).astype(np.float32)
+    xs = np.arange(-5 + 0.1, 20 - 0.1 + 1e-9, 0.1)
+    ys = np.arange(-15 + 0.1, 5 - 0.1 + 1e-9, 0.1)
+    xg, yg = np.meshgrid(xs, ys)
+    X = np.stack([xg.T.ravel(), yg.T.ravel()], 1).astype(np.float32)[::7]
+    M = refpy.RefMap2()
+    nleaves = []
+    for i in range(len(frames)):
+        M.update(thetas, ranges[i], pose6[i])
+        c, n, tr = M.clusters()
+        nleaves.append(len(c))
+    c, n, tr = M.clusters()
+    return dict(thetas=thetas, ranges=ranges, pose6=pose6, X=X, rows=M.test(X), leaves=c, nleaves=np.array(nleaves, np.int32),
+                nsamples=np.int32(len(M.all_samples())))
+
+
 def map3d(seed):
     rng = np.random.default_rng(seed)
     P = H.P3
@@ -121,6 +147,7 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "obs2d.npz"), **obs2d(13))
     np.savez_compressed(os.path.join(HERE, "seq2d.npz"), **seq2d())
     np.savez_compressed(os.path.join(HERE, "map3d.npz"), **map3d(14))
+    np.savez_compressed(os.path.join(HERE, "seq2d_demo.npz"), **seq2d_demo())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

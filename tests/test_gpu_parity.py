@@ -331,3 +331,25 @@ def test_query_on_sample_position_nan_pattern(cabi, oracle):
     fin = ~np.isnan(want)
     assert np.allclose(got[fin], want[fin], rtol=2e-3, atol=1e-5)
     ctx.close()
+
+
+def test_gpismap2d_whole_demo_sequence(cabi):
+    """BASELINE configs[0]: all 28 scans of the reference's 2-D demo (matlab/demo_gpisMap.m) through the drop-in
+    GPisMap: the leaf count after every scan and the final leaf set equal the reference's (leaf assignment is
+    bit-exact), the evaluated mask on the demo grid is identical and f agrees where evaluated."""
+    from gpismap_b200 import hostapi
+    g = dict(np.load(os.path.join(G, "seq2d_demo.npz")))
+    m = hostapi.GPisMap()
+    for i in range(g["ranges"].shape[0]):
+        m.update(g["thetas"], g["ranges"][i], g["pose6"][i])
+        assert m.leaves()[0].shape[0] == g["nleaves"][i], i
+    assert np.array_equal(m.leaves()[0], g["leaves"])
+    s = m.all_samples()
+    assert abs(len(s) - int(g["nsamples"])) <= max(3, 0.01 * len(s))
+    rows = m.test(g["X"])
+    ref = g["rows"]
+    ev = ref[:, 3] < 1.0
+    assert np.array_equal(rows[:, 3] < 1.0, ev)
+    assert ev.sum() > 1000
+    assert np.abs(rows[ev, 0] - ref[ev, 0]).max() < 1e-2 and np.median(np.abs(rows[ev, 0] - ref[ev, 0])) < 1e-4
+    m.close()
