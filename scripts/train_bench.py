@@ -7,7 +7,7 @@ from gpismap_b200 import cabi
 import helpers
 rng = np.random.default_rng(5)
 nleaf = int(sys.argv[1]) if len(sys.argv) > 1 else 296
-print("GPIS_TRAIN_VERSION", os.environ.get("GPIS_TRAIN_VERSION", "2"), "leaves per launch", nleaf)
+print("k_leaf_train, leaves per launch", nleaf)
 for N in (48, 96, 144, 200, 260, 330, 400, 480):
     ctx = cabi.Ctx(dim=3)
     base = helpers.leaf_samples3(N, rng, spread=0.045)
