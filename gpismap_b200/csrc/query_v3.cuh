@@ -420,10 +420,12 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             E3_ACC(1, t_r0, t_r1)   // waiting for the operand U_j
             const float* Uj = U + (size_t)cur.j * 32 * NCOL;
             const bool solo = (cur.part == 0 && cur.split);   // lookahead part: its whole tile was staged at once
-            for (int q = 0; q < 4; ++q) {
+            // One quarter step: prefetch (the next quarter of this visit, or the first step of the next one; a solo
+            // visit owns its stage for all four quarters and prefetches only once), wait for this step's tiles, FMAs.
+            // The slot count / slot index is a compile-time constant of the loop: the dispatch happens once per
+            // visit, not once per step.
+            auto step_pre = [&](int q) {
                 E3_T(t_s0)
-                // what to prefetch during this step: the next quarter of this visit, or the first step of the next
-                // one; a solo visit owns its stage for all four quarters and prefetches only once
                 const bool do_wait = !solo || q == 0;
                 if (do_wait) {
                     bool issued = true;
@@ -442,19 +444,56 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 }
                 E3_T(t_s1)
                 E3_ACC(2, t_s0, t_s1)   // issue + waiting for the staged tiles
-                const float* Bq = Uj + q * 8 * NCOL;
-                // solo: quarter q of the tile sits at stage + q*256 and the micro-kernel adds slot*256 itself
-                const float* As = stg + st * E3_STAGE_FLOATS + (solo ? (q - cur.s_lo) * 256 : 0);
-                if (cur.s_lo == 0 && !solo) qmma_dispatch<CPL, NCOL>(cur.cnt, acc, As, Bq, rg, cg);
-                else qmma_dispatch_one<CPL, NCOL>(cur.s_lo, acc, As, Bq, rg, cg);
+            };
+            auto step_post = [&](int q) {
                 __syncwarp();
                 if (!solo || q == 3) st ^= 1;
-                E3_T(t_s2)
-                E3_ACC(3, t_s1, t_s2)   // FMA work
 #ifdef E3_TIMING
-                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 32 + 8] += cur.cnt; g_e3_timing[warp * 32 + 9] += 1;
-                    g_e3_timing[warp * 32 + 16 + cur.cnt] += t_s2 - t_s1; g_e3_timing[warp * 32 + 24 + cur.cnt] += 1; }
+                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 32 + 8] += cur.cnt; g_e3_timing[warp * 32 + 9] += 1; }
 #endif
+            };
+            auto run_multi = [&](auto cc) {   // slots [0, C) against column j
+                constexpr int C = decltype(cc)::value;
+                for (int q = 0; q < 4; ++q) {
+                    step_pre(q);
+                    qmma_sub<C, CPL, NCOL>(acc, stg + st * E3_STAGE_FLOATS, Uj + q * 8 * NCOL, rg, cg);
+                    step_post(q);
+                }
+            };
+            auto run_solo = [&](auto sc) {    // slot S alone; quarter q of its tile sits at stage + q*256
+                constexpr int S = decltype(sc)::value;
+                for (int q = 0; q < 4; ++q) {
+                    step_pre(q);
+                    qmma_one<S, CPL, NCOL>(acc, stg + st * E3_STAGE_FLOATS + (q - S) * 256, Uj + q * 8 * NCOL, rg, cg);
+                    step_post(q);
+                }
+            };
+            if (solo) {
+                switch (cur.s_lo) {
+#if E3_R >= 4
+                    case 3: run_solo(std::integral_constant<int, 3>{}); break;
+#endif
+#if E3_R >= 3
+                    case 2: run_solo(std::integral_constant<int, 2>{}); break;
+#endif
+#if E3_R >= 2
+                    case 1: run_solo(std::integral_constant<int, 1>{}); break;
+#endif
+                    default: run_solo(std::integral_constant<int, 0>{}); break;
+                }
+            } else {
+                switch (cur.cnt) {
+#if E3_R >= 4
+                    case 4: run_multi(std::integral_constant<int, 4>{}); break;
+#endif
+#if E3_R >= 3
+                    case 3: run_multi(std::integral_constant<int, 3>{}); break;
+#endif
+#if E3_R >= 2
+                    case 2: run_multi(std::integral_constant<int, 2>{}); break;
+#endif
+                    default: run_multi(std::integral_constant<int, 1>{}); break;
+                }
             }
             if (solo) {
                 // row j+1 (slot s_lo) is final: publish it
