@@ -455,7 +455,29 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             auto run_multi = [&](auto cc) {   // slots [0, C) against column j
                 constexpr int C = decltype(cc)::value;
                 for (int q = 0; q < 4; ++q) {
+#ifdef E3_USE_CPASYNC
+                    // the next quarter of this visit: slots [0, C) are known to be active, no predicates
+                    if (q < 3) {
+#pragma unroll
+                        for (int sl = 0; sl < C; ++sl) {
+                            const int ti = sl == 0 ? cur.t0 : sl == 1 ? cur.t1 : sl == 2 ? cur.t2 : cur.t3;
+                            const float* src = tiles + (size_t)ti * GPIS_TILE_ELEMS + (q + 1) * 256 + lane * 4;
+                            float* dst = stg + ((st ^ 1) * E3_R + sl) * 256 + lane * 4;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 128)), "l"(src + 128) : "memory");
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else if (nxt.valid) {
+                        issue(nxt, 0, st ^ 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                    __syncwarp();
+#else
                     step_pre(q);
+#endif
                     qmma_sub<C, CPL, NCOL>(acc, stg + st * E3_STAGE_FLOATS, Uj + q * 8 * NCOL, rg, cg);
                     step_post(q);
                 }
