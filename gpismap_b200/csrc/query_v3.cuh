@@ -484,11 +484,22 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             };
             auto run_solo = [&](auto sc) {    // slot S alone; quarter q of its tile sits at stage + q*256
                 constexpr int S = decltype(sc)::value;
+#ifdef E3_USE_CPASYNC
+                // the whole tile is already in flight: one prefetch (the next visit), one wait, four quarters
+                if (nxt.valid) { issue(nxt, 0, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                for (int q = 0; q < 4; ++q)
+                    qmma_one<S, CPL, NCOL>(acc, stg + st * E3_STAGE_FLOATS + (q - S) * 256, Uj + q * 8 * NCOL, rg, cg);
+                __syncwarp();
+                st ^= 1;
+#else
                 for (int q = 0; q < 4; ++q) {
                     step_pre(q);
                     qmma_one<S, CPL, NCOL>(acc, stg + st * E3_STAGE_FLOATS + (q - S) * 256, Uj + q * 8 * NCOL, rg, cg);
                     step_post(q);
                 }
+#endif
             };
             if (solo) {
                 switch (cur.s_lo) {
