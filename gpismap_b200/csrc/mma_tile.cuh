@@ -78,8 +78,9 @@ __device__ __forceinline__ void qmma_sub(float (&acc)[E3_R][4][CPL], const float
         }
     }
 }
-// one accumulator slot S only (the lookahead part of a split visit)
-template <int S, int CPL, int NCOL>
+// one accumulator slot S only (the lookahead part of a split visit), KS consecutive k (8 = a quarter tile,
+// 32 = the whole tile in one software pipeline)
+template <int S, int CPL, int NCOL, int KS = 8>
 __device__ __forceinline__ void qmma_one(float (&acc)[E3_R][4][CPL], const float* __restrict__ As,
                                          const float* __restrict__ Bq, int rg, int cg) {
     const float* Ap = As + S * 256 + 4 * rg;
@@ -88,10 +89,10 @@ __device__ __forceinline__ void qmma_one(float (&acc)[E3_R][4][CPL], const float
     float4 av[2];
     ld_cols<CPL>(Bp, bv[0]);
     av[0] = *reinterpret_cast<const float4*>(Ap);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
+#pragma unroll 8
+    for (int k = 0; k < KS; ++k) {
         const int cu = k & 1, nx = cu ^ 1;
-        if (k + 1 < 8) {
+        if (k + 1 < KS) {
             ld_cols<CPL>(Bp + (k + 1) * NCOL, bv[nx]);
             av[nx] = *reinterpret_cast<const float4*>(Ap + (k + 1) * 32);
         }

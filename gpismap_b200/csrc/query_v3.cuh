@@ -489,8 +489,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 if (nxt.valid) { issue(nxt, 0, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
                 else asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-                for (int q = 0; q < 4; ++q)
-                    qmma_one<S, CPL, NCOL>(acc, stg + st * E3_STAGE_FLOATS + (q - S) * 256, Uj + q * 8 * NCOL, rg, cg);
+                qmma_one<S, CPL, NCOL, 32>(acc, stg + st * E3_STAGE_FLOATS - S * 256, Uj, rg, cg);
                 __syncwarp();
                 st ^= 1;
 #else
@@ -587,8 +586,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
 #pragma unroll
                 for (int jj = 0; jj < CPL; ++jj) v[0][i][jj] = 0.f;
             const float* Uj = U + (size_t)j * 32 * NCOL;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) qmma_sub<1, CPL, NCOL>(v, stg + st * E3_STAGE_FLOATS + q * 256, Uj + q * 8 * NCOL, rg, cg);
+            qmma_one<0, CPL, NCOL, 32>(v, stg + st * E3_STAGE_FLOATS, Uj, rg, cg);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
