@@ -228,6 +228,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + Eval3Smem::off_bar) + warp * 2;
     float* stg = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_stage) + warp * 2 * E3_STAGE_FLOATS;   // [2][E3_R][256]
+    const uint32_t stg_s = smem_u32(stg) + lane * 16;   // this lane's 16-byte column of the warp's staging area (shared-space address)
     float* red = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_red);
     float* U = reinterpret_cast<float*>(smem_raw + Eval3Smem::off_U);                       // [npad][NCOL]
     uint64_t* ready = reinterpret_cast<uint64_t*>(smem_raw + Eval3Smem::off_ready);  // mbarrier per block row: U_j final
@@ -350,19 +351,19 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     auto issue = [&](const SV& v, int q, int stage) {
         if (v.part == 0 && v.split) {
             const float* src = tiles + (size_t)v.solo_tile * GPIS_TILE_ELEMS + lane * 4;
-            float* dst = stg + stage * E3_STAGE_FLOATS + lane * 4;
+            const uint32_t dst = stg_s + stage * (E3_STAGE_FLOATS * 4);
 #pragma unroll
             for (int h = 0; h < 8; ++h)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + h * 128)), "l"(src + h * 128) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + h * 512), "l"(src + h * 128) : "memory");
         } else {
 #pragma unroll
             for (int sl = 0; sl < E3_R; ++sl) {
                 const int ti = sl == 0 ? v.t0 : sl == 1 ? v.t1 : sl == 2 ? v.t2 : v.t3;
                 if (ti >= 0) {
                     const float* src = tiles + (size_t)ti * GPIS_TILE_ELEMS + q * 256 + lane * 4;
-                    float* dst = stg + (stage * E3_R + sl) * 256 + lane * 4;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 128)), "l"(src + 128) : "memory");
+                    const uint32_t dst = stg_s + (stage * E3_R + sl) * 1024;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 128) : "memory");
                 }
             }
         }
@@ -462,9 +463,9 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                         for (int sl = 0; sl < C; ++sl) {
                             const int ti = sl == 0 ? cur.t0 : sl == 1 ? cur.t1 : sl == 2 ? cur.t2 : cur.t3;
                             const float* src = tiles + (size_t)ti * GPIS_TILE_ELEMS + (q + 1) * 256 + lane * 4;
-                            float* dst = stg + ((st ^ 1) * E3_R + sl) * 256 + lane * 4;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 128)), "l"(src + 128) : "memory");
+                            const uint32_t dst = stg_s + ((st ^ 1) * E3_R + sl) * 1024;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 128) : "memory");
                         }
                         asm volatile("cp.async.commit_group;" ::: "memory");
                         asm volatile("cp.async.wait_group 1;" ::: "memory");
