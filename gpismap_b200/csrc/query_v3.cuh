@@ -330,17 +330,24 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     // first the slot of row j+1 alone, then U_{j+1} is published (ready[j+1] = 1), then the remaining slots —
     // so the next column's operand is available long before the other warps ask for it (lookahead). Consumers
     // spin on ready[j]; there is no block-wide barrier inside the elimination.
-    struct SV { int valid, c, j, part, split, s_lo, cnt, solo_tile, t0, t1, t2, t3; };
+    // a visit record as loaded (6 registers); the packed fields are decoded where they are used
+    struct SV {
+        int j, f, t0, t1, t2, t3;
+        __device__ __forceinline__ int s_lo() const { return f & 7; }
+        __device__ __forceinline__ int cnt() const { return (f >> 3) & 7; }
+        __device__ __forceinline__ int part() const { return (f >> 6) & 1; }
+        __device__ __forceinline__ bool valid() const { return (f >> 8) & 1; }
+        __device__ __forceinline__ int wave() const { return (f >> 16) & 255; }
+        __device__ __forceinline__ bool solo() const { return (f & 0xC0) == 0x80; }   // split && part == 0: the lookahead part
+        __device__ __forceinline__ int solo_tile() const { return max(max(t0, t1), max(t2, t3)); }   // its only active slot
+    };
     const int4* prog = G.recs + G.off[nb * E3_WARPS + warp];
     const int nwaves = prog[0].x;
     const int4* pvis = prog + 2 + 2 * nwaves;
     auto load_sv = [&](int v) {
         const int4 a = __ldg(pvis + 2 * v), b = __ldg(pvis + 2 * v + 1);
         SV r;
-        r.j = a.x;
-        r.s_lo = a.y & 7; r.cnt = (a.y >> 3) & 7; r.part = (a.y >> 6) & 1; r.split = (a.y >> 7) & 1; r.valid = (a.y >> 8) & 1;
-        r.c = (a.y >> 16) & 255;
-        r.solo_tile = a.z;
+        r.j = a.x; r.f = a.y;
         r.t0 = b.x; r.t1 = b.y; r.t2 = b.z; r.t3 = b.w;
         return r;
     };
@@ -349,8 +356,8 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     // this access pattern (profiles/r01). The lookahead part of a split visit (one row, R = 1 work) fetches its
     // whole 4 KB tile at once: its four quarter steps are too short to hide a load each.
     auto issue = [&](const SV& v, int q, int stage) {
-        if (v.part == 0 && v.split) {
-            const float* src = tiles + (size_t)v.solo_tile * GPIS_TILE_ELEMS + lane * 4;
+        if (v.solo()) {
+            const float* src = tiles + (size_t)v.solo_tile() * GPIS_TILE_ELEMS + lane * 4;
             const uint32_t dst = stg_s + stage * (E3_STAGE_FLOATS * 4);
 #pragma unroll
             for (int h = 0; h < 8; ++h)
@@ -372,12 +379,12 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
 #else
     auto issue = [&](const SV& v, int q, int stage) {
         if (lane != 0) return;
-        if (v.part == 0 && v.split) {
+        if (v.solo()) {
             mbar_expect_tx(&bars[stage], GPIS_TILE_BYTES);
-            tma_load_1d(stg + stage * E3_STAGE_FLOATS, tiles + (size_t)v.solo_tile * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[stage]);
+            tma_load_1d(stg + stage * E3_STAGE_FLOATS, tiles + (size_t)v.solo_tile() * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[stage]);
             return;
         }
-        mbar_expect_tx(&bars[stage], (uint32_t)v.cnt * 1024u);
+        mbar_expect_tx(&bars[stage], (uint32_t)v.cnt() * 1024u);
 #pragma unroll
         for (int sl = 0; sl < E3_R; ++sl) {
             const int ti = sl == 0 ? v.t0 : sl == 1 ? v.t1 : sl == 2 ? v.t2 : v.t3;
@@ -391,7 +398,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     int st = 0;
     int vi = 0;
     SV cur = load_sv(0);
-    if (cur.valid) issue(cur, 0, 0);
+    if (cur.valid()) issue(cur, 0, 0);
     if (tid == 0) mbar_arrive(&ready[0]);   // row 0 has nothing to eliminate: B_0 is U_0
 
     for (int c = 0; c < nwaves; ++c) {
@@ -411,16 +418,16 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 }
             }
         }
-        while (cur.valid && cur.c == c) {
+        while (cur.valid() && cur.wave() == c) {
             const SV nxt = load_sv(vi + 1);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(pvis + 2 * (vi + 4)));   // program records: 4 visits per line
             // operand U_j must be final (published by the owner of row j)
             E3_T(t_r0)
-            if (cur.part == 0) mbar_wait(&ready[cur.j], 0u);   // hardware-suspended wait, acquire semantics
+            if (cur.part() == 0) mbar_wait(&ready[cur.j], 0u);   // hardware-suspended wait, acquire semantics
             E3_T(t_r1)
             E3_ACC(1, t_r0, t_r1)   // waiting for the operand U_j
             const float* Uj = U + (size_t)cur.j * 32 * NCOL;
-            const bool solo = (cur.part == 0 && cur.split);   // lookahead part: its whole tile was staged at once
+            const bool solo = cur.solo();   // lookahead part: its whole tile was staged at once
             // One quarter step: prefetch (the next quarter of this visit, or the first step of the next one; a solo
             // visit owns its stage for all four quarters and prefetches only once), wait for this step's tiles, FMAs.
             // The slot count / slot index is a compile-time constant of the loop: the dispatch happens once per
@@ -431,7 +438,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 if (do_wait) {
                     bool issued = true;
                     if (!solo && q < 3) issue(cur, q + 1, st ^ 1);
-                    else if (nxt.valid) issue(nxt, 0, st ^ 1);
+                    else if (nxt.valid()) issue(nxt, 0, st ^ 1);
                     else issued = false;
 #ifdef E3_USE_CPASYNC
                     if (issued) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -450,7 +457,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 __syncwarp();
                 if (!solo || q == 3) st ^= 1;
 #ifdef E3_TIMING
-                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 32 + 8] += cur.cnt; g_e3_timing[warp * 32 + 9] += 1; }
+                if (blockIdx.x == E3_TIMING && lane == 0) { g_e3_timing[warp * 32 + 8] += cur.cnt(); g_e3_timing[warp * 32 + 9] += 1; }
 #endif
             };
             auto run_multi = [&](auto cc) {   // slots [0, C) against column j
@@ -469,7 +476,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                         }
                         asm volatile("cp.async.commit_group;" ::: "memory");
                         asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    } else if (nxt.valid) {
+                    } else if (nxt.valid()) {
                         issue(nxt, 0, st ^ 1);
                         asm volatile("cp.async.wait_group 1;" ::: "memory");
                     } else {
@@ -487,7 +494,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 constexpr int S = decltype(sc)::value;
 #ifdef E3_USE_CPASYNC
                 // the whole tile is already in flight: one prefetch (the next visit), one wait, four quarters
-                if (nxt.valid) { issue(nxt, 0, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+                if (nxt.valid()) { issue(nxt, 0, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
                 else asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
                 qmma_one<S, CPL, NCOL, 32>(acc, stg + st * E3_STAGE_FLOATS - S * 256, Uj, rg, cg);
@@ -502,7 +509,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
 #endif
             };
             if (solo) {
-                switch (cur.s_lo) {
+                switch (cur.s_lo()) {
 #if E3_R >= 4
                     case 3: run_solo(std::integral_constant<int, 3>{}); break;
 #endif
@@ -515,7 +522,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                     default: run_solo(std::integral_constant<int, 0>{}); break;
                 }
             } else {
-                switch (cur.cnt) {
+                switch (cur.cnt()) {
 #if E3_R >= 4
                     case 4: run_multi(std::integral_constant<int, 4>{}); break;
 #endif
@@ -533,7 +540,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 float* Un = U + (size_t)(cur.j + 1) * 32 * NCOL;
 #pragma unroll
                 for (int r = 0; r < E3_R; ++r) {
-                    if (r == cur.s_lo) {
+                    if (r == cur.s_lo()) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             st_cols<CPL>(Un + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
