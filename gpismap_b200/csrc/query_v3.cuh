@@ -48,12 +48,13 @@ struct Eval3Smem {
 // ------------------------------------------------------------------ elimination programs
 // The order in which a warp visits (block row, block column) pairs depends only on (nb, warp). It is generated
 // once on the host (same rules the kernel used to evaluate inline: waves of E3_WAVE block rows, the partial
-// wave first, snake dealing, split visits for the lookahead) and read by the kernel as a table: two int4 per
-// record, uniform loads, no per-visit index arithmetic on the device.
+// wave first, snake dealing, split visits for the lookahead) and read by the kernel as a table with uniform
+// loads, no per-visit index arithmetic on the device.
 //   header  : {nwaves, nvisits, nvar, 0}, {0,0,0,0}
 //   wave c  : {R, 0, 0, 0}, {row of slot 0, 1, 2, 3}                 (slot s = the warp's (R-1-s)-th row, ascending)
-//   visit v : {j, flags, solo tile, nact}, {tile of slot 0, 1, 2, 3}   (tile = index into the leaf's tile array, -1 = idle)
-//             flags: bits 0-2 s_lo, 3-5 cnt, 6 part, 7 split, 8 valid, 16-23 wave
+//   visit v : {flags, tiles of slots 0|1, tiles of slots 2|3, nact}     (one int4; a tile is a 16-bit index into the
+//             leaf's tile array, 0xFFFF = idle slot)
+//             flags: bits 0-2 s_lo, 3-5 cnt, 6 part, 7 split, 8 valid, 16-23 wave, 24-31 column j
 //   4 terminator visits (valid clear), then the rows whose variance product this warp computes, 4 per record
 struct EvalProg {
     const int4* recs;       // all programs
@@ -160,15 +161,13 @@ static inline void e3_emit_program(const E3WarpProg& wp, std::vector<int4>& out)
         out.push_back(make_int4(wp.R[c], 0, 0, 0));
         out.push_back(make_int4(wp.rows[c][0], wp.rows[c][1], wp.rows[c][2], wp.rows[c][3]));
     }
+    auto pack2 = [](int a, int b) { return (int)(((uint32_t)a & 0xFFFFu) | (((uint32_t)b & 0xFFFFu) << 16)); };   // -1 -> 0xFFFF
     for (const E3Visit& v : wp.vis) {
-        const int flags = v.s_lo | (v.cnt << 3) | (v.part << 6) | (v.split << 7) | (1 << 8) | (v.c << 16);
-        out.push_back(make_int4(v.j, flags, v.t[v.s_lo], v.nact));
-        out.push_back(make_int4(v.t[0], v.t[1], v.t[2], v.t[3]));
+        const int flags = v.s_lo | (v.cnt << 3) | (v.part << 6) | (v.split << 7) | (1 << 8) | (v.c << 16) | (v.j << 24);
+        out.push_back(make_int4(flags, pack2(v.t[0], v.t[1]), pack2(v.t[2], v.t[3]), v.nact));
     }
-    for (int k = 0; k < 4; ++k) {   // terminators (valid bit clear); also the landing zone of the look-ahead loads
-        out.push_back(make_int4(0, 0, -1, 0));
-        out.push_back(make_int4(-1, -1, -1, -1));
-    }
+    for (int k = 0; k < 4; ++k)   // terminators (valid bit clear); also the landing zone of the look-ahead loads
+        out.push_back(make_int4(0, -1, -1, 0));
     for (size_t i = 0; i < wp.var_rows.size(); i += 4) {
         int r[4] = {-1, -1, -1, -1};
         for (size_t k = 0; k < 4 && i + k < wp.var_rows.size(); ++k) r[k] = wp.var_rows[i + k];
@@ -330,25 +329,29 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     // first the slot of row j+1 alone, then U_{j+1} is published (ready[j+1] = 1), then the remaining slots —
     // so the next column's operand is available long before the other warps ask for it (lookahead). Consumers
     // spin on ready[j]; there is no block-wide barrier inside the elimination.
-    // a visit record as loaded (6 registers); the packed fields are decoded where they are used
+    // a visit record as loaded (3 registers); the packed fields are decoded where they are used
     struct SV {
-        int j, f, t0, t1, t2, t3;
+        int f; uint32_t t01, t23;
+        __device__ __forceinline__ int j() const { return (int)((uint32_t)f >> 24); }
         __device__ __forceinline__ int s_lo() const { return f & 7; }
         __device__ __forceinline__ int cnt() const { return (f >> 3) & 7; }
         __device__ __forceinline__ int part() const { return (f >> 6) & 1; }
         __device__ __forceinline__ bool valid() const { return (f >> 8) & 1; }
         __device__ __forceinline__ int wave() const { return (f >> 16) & 255; }
         __device__ __forceinline__ bool solo() const { return (f & 0xC0) == 0x80; }   // split && part == 0: the lookahead part
-        __device__ __forceinline__ int solo_tile() const { return max(max(t0, t1), max(t2, t3)); }   // its only active slot
+        __device__ __forceinline__ int tile(int sl) const {                            // -1 = idle slot
+            const uint32_t t = (sl == 0) ? (t01 & 0xFFFFu) : (sl == 1) ? (t01 >> 16) : (sl == 2) ? (t23 & 0xFFFFu) : (t23 >> 16);
+            return t == 0xFFFFu ? -1 : (int)t;
+        }
+        __device__ __forceinline__ int solo_tile() const { return tile(s_lo()); }
     };
     const int4* prog = G.recs + G.off[nb * E3_WARPS + warp];
     const int nwaves = prog[0].x;
     const int4* pvis = prog + 2 + 2 * nwaves;
     auto load_sv = [&](int v) {
-        const int4 a = __ldg(pvis + 2 * v), b = __ldg(pvis + 2 * v + 1);
+        const int4 a = __ldg(pvis + v);
         SV r;
-        r.j = a.x; r.f = a.y;
-        r.t0 = b.x; r.t1 = b.y; r.t2 = b.z; r.t3 = b.w;
+        r.f = a.x; r.t01 = (uint32_t)a.y; r.t23 = (uint32_t)a.z;
         return r;
     };
 #ifdef E3_USE_CPASYNC
@@ -365,7 +368,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         } else {
 #pragma unroll
             for (int sl = 0; sl < E3_R; ++sl) {
-                const int ti = sl == 0 ? v.t0 : sl == 1 ? v.t1 : sl == 2 ? v.t2 : v.t3;
+                const int ti = v.tile(sl);
                 if (ti >= 0) {
                     const float* src = tiles + (size_t)ti * GPIS_TILE_ELEMS + q * 256 + lane * 4;
                     const uint32_t dst = stg_s + (stage * E3_R + sl) * 1024;
@@ -387,7 +390,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         mbar_expect_tx(&bars[stage], (uint32_t)v.cnt() * 1024u);
 #pragma unroll
         for (int sl = 0; sl < E3_R; ++sl) {
-            const int ti = sl == 0 ? v.t0 : sl == 1 ? v.t1 : sl == 2 ? v.t2 : v.t3;
+            const int ti = v.tile(sl);
             if (ti >= 0) tma_load_1d(stg + (stage * E3_R + sl) * 256, tiles + (size_t)ti * GPIS_TILE_ELEMS + q * 256, 1024u, &bars[stage]);
         }
     };
@@ -398,6 +401,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     int st = 0;
     int vi = 0;
     SV cur = load_sv(0);
+    SV nxt = load_sv(1);
     if (cur.valid()) issue(cur, 0, 0);
     if (tid == 0) mbar_arrive(&ready[0]);   // row 0 has nothing to eliminate: B_0 is U_0
 
@@ -419,14 +423,14 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             }
         }
         while (cur.valid() && cur.wave() == c) {
-            const SV nxt = load_sv(vi + 1);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pvis + 2 * (vi + 4)));   // program records: 4 visits per line
+            const SV nxt2 = load_sv(vi + 2);   // two visits ahead: the records come from the L2 (no L1 left beside the
+                                               // shared-memory carve-out) and must not be waited for
             // operand U_j must be final (published by the owner of row j)
             E3_T(t_r0)
-            if (cur.part() == 0) mbar_wait(&ready[cur.j], 0u);   // hardware-suspended wait, acquire semantics
+            if (cur.part() == 0) mbar_wait(&ready[cur.j()], 0u);   // hardware-suspended wait, acquire semantics
             E3_T(t_r1)
             E3_ACC(1, t_r0, t_r1)   // waiting for the operand U_j
-            const float* Uj = U + (size_t)cur.j * 32 * NCOL;
+            const float* Uj = U + (size_t)cur.j() * 32 * NCOL;
             const bool solo = cur.solo();   // lookahead part: its whole tile was staged at once
             // One quarter step: prefetch (the next quarter of this visit, or the first step of the next one; a solo
             // visit owns its stage for all four quarters and prefetches only once), wait for this step's tiles, FMAs.
@@ -468,7 +472,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                     if (q < 3) {
 #pragma unroll
                         for (int sl = 0; sl < C; ++sl) {
-                            const int ti = sl == 0 ? cur.t0 : sl == 1 ? cur.t1 : sl == 2 ? cur.t2 : cur.t3;
+                            const int ti = cur.tile(sl);
                             const float* src = tiles + (size_t)ti * GPIS_TILE_ELEMS + (q + 1) * 256 + lane * 4;
                             const uint32_t dst = stg_s + ((st ^ 1) * E3_R + sl) * 1024;
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -537,7 +541,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             }
             if (solo) {
                 // row j+1 (slot s_lo) is final: publish it
-                float* Un = U + (size_t)(cur.j + 1) * 32 * NCOL;
+                float* Un = U + (size_t)(cur.j() + 1) * 32 * NCOL;
 #pragma unroll
                 for (int r = 0; r < E3_R; ++r) {
                     if (r == cur.s_lo()) {
@@ -547,9 +551,10 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ready[cur.j + 1]);   // release: the stores above are visible to waiters
+                if (lane == 0) mbar_arrive(&ready[cur.j() + 1]);   // release: the stores above are visible to waiters
             }
             cur = nxt;
+            nxt = nxt2;
             ++vi;
         }
     }
@@ -567,7 +572,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
         static_assert(E3_R == 4, "a stage must hold one full tile");
         // rows assigned to this warp by the program (not necessarily its own: see e3_assign_variance)
         const int nvar = prog[0].z;
-        const int* vrows = reinterpret_cast<const int*>(pvis + 2 * (prog[0].y + 4));
+        const int* vrows = reinterpret_cast<const int*>(pvis + (prog[0].y + 4));
         auto issue_d = [&](int j, int s2) {
             if (lane == 0) {
                 mbar_expect_tx(&bars[s2], GPIS_TILE_BYTES);

@@ -27,14 +27,20 @@ def _program(lib, nb, warp):
     waves = [(int(r[2 + 2 * c, 0]), [int(v) for v in r[3 + 2 * c]]) for c in range(nwaves)]
     v0 = 2 + 2 * nwaves
     visits = []
+
+    def tile16(word, hi):
+        t = (int(word) >> 16) & 0xFFFF if hi else int(word) & 0xFFFF
+        return -1 if t == 0xFFFF else t
+
     for v in range(nvis):
-        a, b = r[v0 + 2 * v], r[v0 + 2 * v + 1]
-        f = int(a[1])
-        visits.append(dict(j=int(a[0]), s_lo=f & 7, cnt=(f >> 3) & 7, part=(f >> 6) & 1, split=(f >> 7) & 1,
-                           valid=(f >> 8) & 1, wave=(f >> 16) & 255, solo_tile=int(a[2]), tiles=[int(t) for t in b]))
+        a = r[v0 + v]
+        f = int(a[0]) & 0xFFFFFFFF
+        tiles = [tile16(a[1], 0), tile16(a[1], 1), tile16(a[2], 0), tile16(a[2], 1)]
+        visits.append(dict(j=(f >> 24) & 255, s_lo=f & 7, cnt=(f >> 3) & 7, part=(f >> 6) & 1, split=(f >> 7) & 1,
+                           valid=(f >> 8) & 1, wave=(f >> 16) & 255, solo_tile=tiles[f & 7], tiles=tiles))
     for t in range(4):   # terminators
-        assert ((int(r[v0 + 2 * (nvis + t), 1]) >> 8) & 1) == 0
-    var_rows = [int(x) for x in r[v0 + 2 * (nvis + 4):].ravel()[:nvar]]
+        assert ((int(r[v0 + nvis + t, 0]) >> 8) & 1) == 0
+    var_rows = [int(x) for x in r[v0 + nvis + 4:].ravel()[:nvar]]
     return waves, visits, var_rows
 
 
