@@ -16,7 +16,7 @@
 // slower here). Synchronisation is dataflow: one mbarrier per block row, armed when the row's tile of U is final
 // and written to shared memory (exactly once); the owner of row j+1 applies column j to that row first and
 // publishes it before touching its other rows (lookahead). There is no block-wide barrier inside the elimination.
-// The order of visits is not computed on the device: the host generates, per (nb, warp), a program of 32-byte
+// The order of visits is not computed on the device: the host generates, per (nb, warp), a program of 16-byte
 // records (e3_build_warp) and a list of the rows whose variance product the warp computes (e3_assign_variance);
 // tests/test_eval_programs.py checks coverage, publish protocol and deadlock freedom of those programs on the CPU.
 #pragma once
