@@ -277,23 +277,20 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
             const float r = sqrtf(s2);
             const DF e = exp_df(-P.a * r);
             float* col = U + 4 * qi;
-            col[k * NCOL] = kf_val(r, P.a, e);
-            float k1[DIM];
+            float k1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < DIM; ++c) { k1[c] = kf1_val(d[c], P.a, e); col[k * NCOL + 1 + c] = k1[c]; }
+            for (int c = 0; c < DIM; ++c) k1[c] = kf1_val(d[c], P.a, e);
+            // one 16-byte store per row: [k, dk/dx, dk/dy, dk/dz] (2-D: the fourth entry stays 0)
+            *reinterpret_cast<float4*>(col + k * NCOL) = make_float4(kf_val(r, P.a, e), k1[0], k1[1], k1[2]);
             if (g >= 0) {
-                float k2[DIM][DIM];   // symmetric: (c, e2) and (e2, c) are the same expression (covFnc.cpp:300-309)
+                float k2[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // symmetric (covFnc.cpp:300-309)
 #pragma unroll
                 for (int c = 0; c < DIM; ++c)
 #pragma unroll
                     for (int e2 = c; e2 < DIM; ++e2) k2[c][e2] = k2[e2][c] = kf2_val(r, d[c], d[e2], c == e2 ? 1.f : 0.f, P.a, e);
 #pragma unroll
-                for (int c = 0; c < DIM; ++c) {
-                    float* rowp = col + (size_t)(N + c * ng + g) * NCOL;
-                    rowp[0] = -k1[c];
-#pragma unroll
-                    for (int e2 = 0; e2 < DIM; ++e2) rowp[1 + e2] = k2[c][e2];
-                }
+                for (int c = 0; c < DIM; ++c)
+                    *reinterpret_cast<float4*>(col + (size_t)(N + c * ng + g) * NCOL) = make_float4(-k1[c], k2[c][0], k2[c][1], k2[c][2]);
             }
         }
     };
@@ -317,7 +314,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                 W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + c] = s;
             }
         }
-        __syncthreads();
+        __syncthreads();   // `red` is reused by the final reduction: a warp without rows (tiny leaves) gets there at once
     }
 
     E3_T(t_elim0)
