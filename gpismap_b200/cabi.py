@@ -36,6 +36,7 @@ class Stats(C.Structure):
         ("arena_bytes_reserved", C.c_int64),
         ("last_train_leaves", C.c_int64), ("last_train_sum_N", C.c_int64), ("last_train_sum_n", C.c_int64),
         ("last_train_flops", C.c_double), ("last_train_bytes", C.c_double), ("last_train_ms", C.c_float),
+        ("last_train_skipped", C.c_int32),
         ("last_query_n", C.c_int64), ("last_query_evals", C.c_int64),
         ("last_query_flops", C.c_double), ("last_query_bytes_gather", C.c_double),
         ("last_query_bytes_compulsory", C.c_double), ("last_query_ms", C.c_float), ("last_query_eval_ms", C.c_float),

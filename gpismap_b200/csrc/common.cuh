@@ -99,7 +99,7 @@ struct QueryParams {
     float cluster_half, search_half, var_thre;
     float var_preset;   // (float)(1.0 + map_noise)            GPisMap3.cpp:816
     float a;            // (float)(sqrt(3)/scale)              covFnc.cpp:263
-    float prior_f;      // 3D: 1.001, 2D: 1.01                 OnGPIS.cpp:204,235
+    double prior_f;     // 3D: 1.001, 2D: 1.01 (double literals) OnGPIS.cpp:203,235
     double prior_g;     // three_over_scale + 0.001 / + 0.1    OnGPIS.cpp:205-212,236-237
     double inv_pitch;   // 1 / (2*cluster_half)
     int root_min[3];    // root box for DFS tie-breaks (gpis_rebase)

@@ -20,7 +20,7 @@
 #include "leaf_train.cuh"
 #include "obs_gp.cuh"
 #include "query.cuh"
-#include "query_v2.cuh"
+#include "query_group.cuh"
 #include "query_v3.cuh"
 
 using namespace gpis;
@@ -144,6 +144,7 @@ struct gpis_ctx {
     // scratch
     void* d_scratch = nullptr; uint64_t scratch_bytes = 0;       // generic upload buffer
     void* d_scratch2 = nullptr; uint64_t scratch2_bytes = 0;
+    void* d_jobs = nullptr; uint64_t jobs_bytes = 0;             // training jobs + status
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
@@ -287,8 +288,8 @@ static void derive_params(gpis_ctx* ctx) {
     q.var_preset = (float)(1.0 + (double)c.map_noise);                 // GPisMap3.cpp:816
     q.a = (float)(std::sqrt(3.0) / (double)c.map_scale);               // covFnc.cpp:263
     const float three_over_scale = (float)(3.0 / (double)(c.map_scale * c.map_scale));  // OnGPIS.h:58
-    if (c.dim == 3) { q.prior_f = 1.001f; q.prior_g = (double)three_over_scale + 0.001; }   // OnGPIS.cpp:203-212
-    else            { q.prior_f = 1.01f;  q.prior_g = (double)three_over_scale + 0.1; }     // OnGPIS.cpp:235-237
+    if (c.dim == 3) { q.prior_f = 1.001; q.prior_g = (double)three_over_scale + 0.001; }   // OnGPIS.cpp:203-212
+    else            { q.prior_f = 1.01;  q.prior_g = (double)three_over_scale + 0.1; }     // OnGPIS.cpp:235-237
     q.inv_pitch = 1.0 / (2.0 * (double)c.cluster_half);
     q.root_min[0] = q.root_min[1] = q.root_min[2] = -(1 << 19);
     q.levels = 20;
@@ -369,7 +370,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     for (auto& c : ctx->chunks) cudaFree(c.base);
     cudaFree(ctx->T.keys); cudaFree(ctx->T.vals); cudaFree(ctx->T.centre); cudaFree(ctx->T.cell);
     cudaFree(ctx->T.rec); cudaFree(ctx->T.meta); cudaFree(ctx->T.lo); cudaFree(ctx->T.hi);
-    cudaFree(ctx->d_scratch); cudaFree(ctx->d_scratch2);
+    cudaFree(ctx->d_scratch); cudaFree(ctx->d_scratch2); cudaFree(ctx->d_jobs);
     cudaFree(ctx->W.cand); cudaFree(ctx->W.tie); cudaFree(ctx->W.evalout); cudaFree(ctx->W.pairs); cudaFree(ctx->W.counters);
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
     cudaFree(const_cast<int4*>(ctx->prog.recs)); cudaFree(const_cast<int32_t*>(ctx->prog.off));
@@ -523,6 +524,39 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
     return 0;
 }
 
+// Launch K1 on a batch of jobs whose records are allocated and whose samples sit in d_smp (device). Jobs are
+// sorted biggest-first (one CTA per leaf, the hardware scheduler balances the tail). status_host (optional,
+// job order) receives the non-positive-pivot counts.
+static int train_jobs(gpis_ctx* ctx, std::vector<TrainJob>& jobs, const float* d_smp, int maxN, int maxnb,
+                      int32_t* status_host, float* ms_out) {
+    *ms_out = 0.f;
+    if (jobs.empty()) return 0;
+    std::vector<int> order(jobs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].n > jobs[b].n; });
+    std::vector<TrainJob> sorted(jobs.size());
+    for (size_t i = 0; i < order.size(); ++i) sorted[i] = jobs[order[i]];
+    const uint64_t b_jobs = align_up(sorted.size() * sizeof(TrainJob), 256);
+    const uint64_t b_st = align_up(sorted.size() * sizeof(int32_t), 256);
+    int rc = ensure(ctx, &ctx->d_jobs, &ctx->jobs_bytes, b_jobs + b_st);
+    if (rc) return rc;
+    TrainJob* d_jobs = (TrainJob*)ctx->d_jobs;
+    int32_t* d_st = (int32_t*)((unsigned char*)ctx->d_jobs + b_jobs);
+    CK(cudaMemcpyAsync(d_jobs, sorted.data(), sorted.size() * sizeof(TrainJob), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = launch_leaf_train(ctx->stream, d_jobs, (int)sorted.size(), d_smp, ctx->tp, d_st, maxN, maxnb, ctx->err);
+    if (rc) return rc;
+    ctx->st.kernel_launches++;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    std::vector<int32_t> st(sorted.size());
+    CK(cudaMemcpyAsync(st.data(), d_st, sorted.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(ms_out, ctx->ev[0], ctx->ev[1]));
+    if (status_host)
+        for (size_t i = 0; i < order.size(); ++i) status_host[order[i]] = st[i];
+    return 0;
+}
+
 int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres,
                        const int32_t* offsets, const float* samples, int32_t* status) {
     if (!ctx || n_leaves < 0) return GPIS_ERR_ARG;
@@ -530,20 +564,49 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
     if (!cells || !centres || !offsets || !samples) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
+
+    // ---- pass 1: validate and size every leaf; nothing is mutated yet. A leaf beyond the kernel's capacity
+    // (the reference has no limit, OnGPIS.cpp:91-149) is skipped — it keeps whatever GP it had — and flagged in
+    // status[]; the rest of the batch is trained.
+    struct Plan { int N, ng, n, nb; bool train; uint64_t rec, rb; };
+    std::vector<Plan> plan(n_leaves);
+    int skipped = 0;
+    for (int i = 0; i < n_leaves; ++i) {
+        const int N = offsets[i + 1] - offsets[i];
+        if (N < 0 || offsets[i] < 0) { ctx->err = "offsets must be non-negative and non-decreasing"; return GPIS_ERR_ARG; }
+        Plan& pl = plan[i];
+        pl = Plan{N, 0, 0, 0, false, 0, 0};
+        if (N == 0) continue;   // GPisMap3.cpp:710: nothing in range -> the leaf keeps whatever GP it had
+        if (N > GPIS_MAX_SAMPLES) { ++skipped; continue; }
+        int ng = 0;
+        for (int k = 0; k < N; ++k) ng += grad_valid(samples + (size_t)(offsets[i] + k) * w9, dim) ? 1 : 0;
+        pl.ng = ng; pl.n = N + dim * ng; pl.nb = (pl.n + 31) / 32;
+        if (pl.n > GPIS_MAX_N) { ++skipped; continue; }
+        pl.train = true;
+        pl.rb = rec_bytes(N, pl.nb);
+    }
+    // ---- pass 2: reserve table space and every record; roll back on failure
     int rc = table_reserve(ctx, n_leaves);
     if (rc) return rc;
-
+    for (int i = 0; i < n_leaves; ++i) {
+        if (!plan[i].train) continue;
+        rc = arena_alloc(ctx, plan[i].rb, &plan[i].rec);
+        if (rc) {
+            for (int k = 0; k < i; ++k) if (plan[k].train) arena_free(ctx, plan[k].rec, plan[k].rb);
+            return rc;
+        }
+    }
+    // ---- pass 3: upload, train, then install (queries never see a half-built record)
     std::vector<TrainJob> jobs;
     std::vector<int> job_leaf;
     std::vector<SlotUpdate> ups;
     std::vector<std::pair<uint64_t, uint64_t>> to_free;
+    std::vector<std::pair<uint64_t, int>> installs;   // key, plan index
     double flops = 0, bytes = 0;
     int64_t sumN = 0, sumn = 0;
     int maxN = 1, maxnb = 1;
     for (int i = 0; i < n_leaves; ++i) {
-        const int N = offsets[i + 1] - offsets[i];
-        if (N < 0) { ctx->err = "offsets must be non-decreasing"; return GPIS_ERR_ARG; }
-        if (N > GPIS_MAX_SAMPLES) { ctx->err = "leaf exceeds GPIS_MAX_SAMPLES"; return GPIS_ERR_CAPACITY; }
+        const Plan& pl = plan[i];
         const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
         auto it = ctx->leaves.find(key);
         if (it == ctx->leaves.end()) {
@@ -553,76 +616,59 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
         }
         HostLeaf& hl = it->second;
         set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
-        if (status) status[i] = 0;
-        if (N == 0) {  // GPisMap3.cpp:710: nothing in range -> the leaf keeps whatever GP it had
+        if (status) status[i] = (pl.N > 0 && !pl.train) ? (int32_t)GPIS_ERR_CAPACITY : 0;
+        if (!pl.train) {   // registered (non-empty) but not retrained
             ups.push_back(make_update(key, hl));
             continue;
         }
-        int ng = 0;
-        for (int k = 0; k < N; ++k) ng += grad_valid(samples + (size_t)(offsets[i] + k) * w9, dim) ? 1 : 0;
-        const int n = N + dim * ng, nb = (n + 31) / 32;
-        if (n > GPIS_MAX_N) { ctx->err = "leaf exceeds GPIS_MAX_N"; return GPIS_ERR_CAPACITY; }
-        uint64_t rec = 0;
-        const uint64_t rb = rec_bytes(N, nb);
-        rc = arena_alloc(ctx, rb, &rec);
-        if (rc) return rc;
-        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
-        hl.rec = rec; hl.rec_bytes = rb; hl.N = N; hl.ng = ng; hl.n = n; hl.nb = nb;
         TrainJob j{};
-        j.rec = rec; j.sample_off = offsets[i]; j.N = N; j.ng = ng; j.n = n; j.nb = nb; j.slot = hl.slot;
+        j.rec = pl.rec; j.sample_off = offsets[i]; j.N = pl.N; j.ng = pl.ng; j.n = pl.n; j.nb = pl.nb; j.slot = hl.slot;
         for (int c = 0; c < 3; ++c) { j.cell[c] = hl.cell[c]; j.centre[c] = hl.centre[c]; j.lo[c] = hl.lo[c]; j.hi[c] = hl.hi[c]; }
         jobs.push_back(j);
         job_leaf.push_back(i);
-        ups.push_back(make_update(key, hl));
-        ctx->dirty_keys.push_back(key);
-        flops += (double)n * n * n / 3.0 + 2.0 * n * n + 30.0 * N * N;
-        bytes += 52.0 * N + 4.0 * n + 2.0 * n * (n + 1.0);
-        sumN += N; sumn += n;
-        maxN = std::max(maxN, N); maxnb = std::max(maxnb, nb);
+        installs.push_back({key, i});
+        flops += (double)pl.n * pl.n * pl.n / 3.0 + 2.0 * pl.n * pl.n + 30.0 * pl.N * pl.N;
+        bytes += 52.0 * pl.N + 4.0 * pl.n + 2.0 * pl.n * (pl.n + 1.0);
+        sumN += pl.N; sumn += pl.n;
+        maxN = std::max(maxN, pl.N); maxnb = std::max(maxnb, pl.nb);
+    }
+    float ms = 0.f;
+    if (!jobs.empty()) {
+        const uint64_t nsamp = (uint64_t)offsets[n_leaves];
+        rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, align_up(nsamp * w9 * sizeof(float), 256));
+        if (rc == 0) {
+            cudaError_t e = cudaMemcpyAsync(ctx->d_scratch, samples, nsamp * w9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { ctx->err = std::string("sample upload: ") + cudaGetErrorString(e); rc = GPIS_ERR_CUDA; }
+        }
+        std::vector<int32_t> st(jobs.size(), 0);
+        if (rc == 0) rc = train_jobs(ctx, jobs, (const float*)ctx->d_scratch, maxN, maxnb, st.data(), &ms);
+        if (rc) {   // nothing was installed: the leaves keep their previous records
+            for (const Plan& pl : plan) if (pl.train) arena_free(ctx, pl.rec, pl.rb);
+            apply_updates(ctx, ups);
+            return rc;
+        }
+        if (status)
+            for (size_t i = 0; i < jobs.size(); ++i) status[job_leaf[i]] = st[i];
+    }
+    for (auto& in : installs) {
+        HostLeaf& hl = ctx->leaves[in.first];
+        const Plan& pl = plan[in.second];
+        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
+        hl.rec = pl.rec; hl.rec_bytes = pl.rb; hl.N = pl.N; hl.ng = pl.ng; hl.n = pl.n; hl.nb = pl.nb;
+        ups.push_back(make_update(in.first, hl));
+        ctx->dirty_keys.push_back(in.first);
     }
     ctx->max_nb = std::max(ctx->max_nb, maxnb);
     ctx->max_N = std::max(ctx->max_N, maxN);
-
-    float ms = 0.f;
-    if (!jobs.empty()) {
-        // biggest systems first: one CTA per leaf, the hardware scheduler balances the tail
-        std::vector<int> order(jobs.size());
-        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].n > jobs[b].n; });
-        std::vector<TrainJob> sorted(jobs.size());
-        for (size_t i = 0; i < order.size(); ++i) sorted[i] = jobs[order[i]];
-        const uint64_t nsamp = (uint64_t)offsets[n_leaves];
-        const uint64_t b_jobs = align_up(sorted.size() * sizeof(TrainJob), 256);
-        const uint64_t b_smp = align_up(nsamp * w9 * sizeof(float), 256);
-        const uint64_t b_st = align_up(sorted.size() * sizeof(int32_t), 256);
-        rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, b_jobs + b_smp + b_st);
-        if (rc) return rc;
-        unsigned char* base = (unsigned char*)ctx->d_scratch;
-        TrainJob* d_jobs = (TrainJob*)base;
-        float* d_smp = (float*)(base + b_jobs);
-        int32_t* d_st = (int32_t*)(base + b_jobs + b_smp);
-        CK(cudaMemcpyAsync(d_jobs, sorted.data(), sorted.size() * sizeof(TrainJob), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_smp, samples, nsamp * w9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        const int smem = TrainSmem::total(maxN, maxnb);
-        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        k_leaf_train<<<(int)sorted.size(), TRAIN_THREADS, smem, ctx->stream>>>(d_jobs, d_smp, ctx->tp, d_st);
-        ctx->st.kernel_launches++;
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        std::vector<int32_t> st(sorted.size());
-        CK(cudaMemcpyAsync(st.data(), d_st, sorted.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-        if (status)
-            for (size_t i = 0; i < order.size(); ++i) status[job_leaf[order[i]]] = st[i];
-    }
-    rc = apply_updates(ctx, ups);   // install after training: queries never see a half-built record
+    rc = apply_updates(ctx, ups);
     if (rc) return rc;
     for (auto& f : to_free) arena_free(ctx, f.first, f.second);
     ctx->st.last_train_leaves = (int64_t)jobs.size();
     ctx->st.last_train_sum_N = sumN; ctx->st.last_train_sum_n = sumn;
     ctx->st.last_train_flops = flops; ctx->st.last_train_bytes = bytes;
     ctx->st.last_train_ms = ms;
+    ctx->st.last_train_skipped = skipped;
+    if (skipped) ctx->err = "gpis_leaves_update: " + std::to_string(skipped) + " leaf/leaves exceed GPIS_MAX_SAMPLES / GPIS_MAX_N and were not retrained (see status[])";
     return GPIS_OK;
 }
 
@@ -899,6 +945,21 @@ int gpis_obs_train_1d(gpis_ctx* ctx, const float* theta, const float* f, int N) 
     return GPIS_OK;
 }
 
+// Batched ObsGP*::test on device-resident points: bucket by tile, then one CTA per (tile, chunk).
+static int obs_test_device(gpis_ctx* ctx, const float* d_x, int m, float* d_val, float* d_var, int32_t* d_tile,
+                           int32_t* d_order, int32_t* d_count, int32_t* d_start, int32_t* d_cursor) {
+    const int nt = ctx->op.ntiles;
+    if (nt < 1 || m < 1) return 0;
+    CK(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * nt, ctx->stream));
+    k_obs_locate<<<(m + 255) / 256, 256, 0, ctx->stream>>>(d_x, m, ctx->obs_b0, ctx->obs_b1, ctx->obs_tiles, ctx->op, d_tile, d_count, d_var);
+    k_obs_scan<<<1, 1024, 0, ctx->stream>>>(d_count, nt, d_start, d_cursor);
+    k_obs_scatter<<<(m + 255) / 256, 256, 0, ctx->stream>>>(d_tile, m, d_cursor, d_order);
+    k_obs_test_grouped<<<dim3(nt, OBS_TEST_CHUNKS), OBS_TEST_THREADS, 0, ctx->stream>>>(d_x, d_start, d_order, ctx->obs_tiles, ctx->op, d_val, d_var);
+    ctx->st.kernel_launches += 4;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, float* var) {
     if (!ctx || !xt || !val || !var || m < 0) return GPIS_ERR_ARG;
     if (m == 0) return GPIS_OK;
@@ -906,18 +967,23 @@ int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, floa
     if (d != ctx->op.d) return GPIS_OK;                       // ObsGP.cpp:412: wrong input dimension
     CK(cudaSetDevice(ctx->cfg.device));
     const uint64_t bx = align_up(sizeof(float) * (uint64_t)d * m, 256), bv = align_up(sizeof(float) * (uint64_t)m, 256);
-    int rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, bx + 2 * bv);
+    const int nt = ctx->op.ntiles;
+    const uint64_t bt = align_up(sizeof(int32_t) * (uint64_t)(nt + 1), 256);
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, bx + 4 * bv + 3 * bt);
     if (rc) return rc;
-    float* d_x = (float*)ctx->d_scratch;
-    float* d_val = (float*)((unsigned char*)ctx->d_scratch + bx);
-    float* d_var = (float*)((unsigned char*)ctx->d_scratch + bx + bv);
+    unsigned char* base = (unsigned char*)ctx->d_scratch;
+    float* d_x = (float*)base;
+    float* d_val = (float*)(base + bx);
+    float* d_var = (float*)(base + bx + bv);
+    int32_t* d_tile = (int32_t*)(base + bx + 2 * bv);
+    int32_t* d_order = (int32_t*)(base + bx + 3 * bv);
+    int32_t* d_count = (int32_t*)(base + bx + 4 * bv);
+    int32_t* d_start = (int32_t*)(base + bx + 4 * bv + bt);
+    int32_t* d_cursor = (int32_t*)(base + bx + 4 * bv + 2 * bt);
     CK(cudaMemcpyAsync(d_x, xt, sizeof(float) * (uint64_t)d * m, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_val, val, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
-    const int warps_per_block = 8;
-    k_obs_test<<<(m + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->stream>>>(
-        d_x, m, ctx->obs_b0, ctx->obs_b1, ctx->obs_tiles, ctx->op, d_val, d_var);
-    ctx->st.kernel_launches++;
-    CK(cudaGetLastError());
+    rc = obs_test_device(ctx, d_x, m, d_val, d_var, d_tile, d_order, d_count, d_start, d_cursor);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(val, d_val, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(var, d_var, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1045,7 +1111,7 @@ int gpis_debug_program(int nb, int warp, int32_t* out, int cap) {
 }
 
 int gpis_set_eval_version(gpis_ctx* ctx, int v) {
-    if (!ctx || v < 1 || v > 3) return GPIS_ERR_ARG;
+    if (!ctx || (v != 1 && v != 3)) return GPIS_ERR_ARG;
     ctx->eval_version = v;
     return GPIS_OK;
 }

@@ -15,6 +15,7 @@
 // Bound: FP32 FMA pipe (n^3/3 flops vs ~2n^2 compulsory bytes). No tensor cores: these are
 // independent small factorizations in fp32 with a 1e-4 parity contract.
 #pragma once
+#include <string>
 #include <type_traits>
 
 #include "common.cuh"
@@ -473,7 +474,7 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
     K1_T(3)
     // ---------------------------------------------------------------- E. query form of the factor
     // Off-diagonal tiles are rewritten in place as G(i,j) = L(i,j) inv(Ljj): the query's block
-    // elimination then needs no per-block triangular solve on its dependency chain (query_v2.cuh).
+    // elimination then needs no per-block triangular solve on its dependency chain (query_v3.cuh).
     // Diagonal tiles keep Ljj; inv(Ljj) stays in the dinv array.
     for (int bj = 0; bj + 1 < nb; ++bj) {
         // dinv_s <- row-major image of inv(Ljj): element (k, c) at k*32 + c
@@ -510,6 +511,16 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         h->cell[3] = 0; h->centre[3] = 0.f; h->lo[3] = 0.f; h->hi[3] = 0.f;
         if (status) status[blockIdx.x] = bad_total;
     }
+}
+
+// One CTA per job; dynamic shared memory sized for the largest leaf of the batch.
+static inline int launch_leaf_train(cudaStream_t st, const TrainJob* d_jobs, int njobs, const float* d_samples,
+                                    const TrainParams& P, int32_t* d_status, int maxN, int maxnb, std::string& err) {
+    if (njobs <= 0) return 0;
+    k_leaf_train<<<njobs, TRAIN_THREADS, TrainSmem::total(maxN, maxnb), st>>>(d_jobs, d_samples, P, d_status);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("k_leaf_train: ") + cudaGetErrorString(e); return -2; }
+    return 0;
 }
 
 }  // namespace gpis

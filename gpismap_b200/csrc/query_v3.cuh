@@ -28,7 +28,7 @@
 #include "common.cuh"
 #include "mma_tile.cuh"
 #include "query.cuh"
-#include "query_v2.cuh"
+#include "query_group.cuh"
 
 namespace gpis {
 
@@ -643,14 +643,12 @@ static inline int query_eval_init(std::string& err) {
     cudaError_t e = cudaFuncSetAttribute(k_eval_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_v3<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(k_eval_*): ") + cudaGetErrorString(e); return -2; }
     return 0;
 }
 
 // Buckets the npairs work items in W.pairs by leaf and evaluates them. *d_sort is a grow-only device
-// buffer owned by the context. version: 1 = one CTA per pair, 2 = first grouped kernel (4x8 lane tile),
-// 3 = production kernel.
+// buffer owned by the context. version: 1 = one CTA per pair (k_eval_v1), otherwise the production kernel.
 static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable& T, const QueryParams& P,
                              const QueryWork& W, int npairs, int nslots, int max_nb, int32_t** d_sort,
                              int64_t* sort_cap, int64_t* launches, std::string& err, double* d_acc, int version,
@@ -693,19 +691,6 @@ static inline int query_eval(cudaStream_t st, const float* d_x, const LeafTable&
         k_eval_v1<<<npairs, EVAL1_THREADS, v1_smem, st>>>(d_x, T, P, W, S.sorted);
         *launches += 1;
         CK2(cudaGetLastError());
-        return 0;
-    }
-    if (version == 2 && Eval2Smem::total(max_nb) <= 227 * 1024) {
-        k_make_items<<<(nslots + 255) / 256, 256, 0, st>>>(S, nslots);
-        *launches += 1;
-        int32_t nitems = 0;
-        CK2(cudaMemcpyAsync(&nitems, S.totals, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CK2(cudaStreamSynchronize(st));
-        if (nitems > 0) {
-            k_eval_v2<<<nitems, EVAL2_THREADS, Eval2Smem::total(max_nb), st>>>(d_x, T, P, W, S);
-            *launches += 1;
-            CK2(cudaGetLastError());
-        }
         return 0;
     }
     k_make_items_classed<<<(nslots + 255) / 256, 256, 0, st>>>(S, T, nslots, E3_NB_A, E3_NB_M, E3_NB_B);

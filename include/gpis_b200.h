@@ -84,7 +84,12 @@ int gpis_device(const gpis_ctx* ctx);
  *   samples  offsets[n] x (2*dim+3) floats: pos[dim], grad[dim], val, pose_sig, grad_sig, in the
  *            tree's QueryRange DFS order (octree.cpp:777-804) — that order is the row order of K
  *   status   n_leaves         out, optional: number of non-positive Cholesky pivots (the
- *                             reference never checks LLT::info(), OnGPIS.cpp:139)
+ *                             reference never checks LLT::info(), OnGPIS.cpp:139), or GPIS_ERR_CAPACITY
+ *                             for a leaf beyond GPIS_MAX_SAMPLES / GPIS_MAX_N: such a leaf is registered
+ *                             but not retrained (it keeps its previous GP), the rest of the batch is
+ *                             trained and the call still returns GPIS_OK (gpis_last_error has a note).
+ * Every leaf is validated and every record reserved before anything is mutated: on an error return
+ * the table, the arena and the installed GPs are as before the call.
  * A leaf with an empty sample range is only registered as non-empty/untrained (the reference
  * skips training when QueryRange returns nothing, GPisMap3.cpp:710). */
 int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres,
@@ -168,6 +173,7 @@ typedef struct gpis_stats {
     double last_train_flops;   /* sum n^3/3 + 2n^2 + 30N^2 */
     double last_train_bytes;   /* sum 52N + 4n + 2n(n+1) */
     float last_train_ms;       /* CUDA-event time of the training kernels */
+    int32_t last_train_skipped; /* leaves beyond GPIS_MAX_SAMPLES / GPIS_MAX_N that were not retrained */
     /* last gpis_query* */
     int64_t last_query_n, last_query_evals; /* evaluated (query, leaf) pairs */
     double last_query_flops;   /* sum 4n^2 + 16n + 80N over evaluations */
@@ -182,8 +188,9 @@ typedef struct gpis_stats {
 int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out);
 
 /* ---- development and test aids (not part of the drop-in surface) ------------------------------
- * gpis_set_eval_version: 3 = production evaluation kernel (k_eval_v3, default), 2 = first grouped
- *   kernel, 1 = one CTA per (query, leaf) pair; the parity tests run all three.
+ * gpis_set_eval_version: 3 = production evaluation kernel (k_eval_v3, default), 1 = one CTA per
+ *   (query, leaf) pair (k_eval_v1, also the fallback for leaves beyond k_eval_v3's shared memory);
+ *   the parity tests run both.
  * gpis_debug_program: the host-generated visit program of k_eval_v3 for a leaf of nb block rows and
  *   one warp, as int32 words (layout: gpismap_b200/csrc/query_v3.cuh); needs no device. Returns the
  *   word count (also when cap is too small), -1 on bad arguments. tests/test_eval_programs.py checks

@@ -263,6 +263,34 @@ void ref3_update_timed(void* m_, float* depth, int N, const float* pose12, doubl
     m->updateGPs();
     phases[4] = now_s() - t4;
 }
+// GPisMap3::update without its last step: the samples of the map depend only on the observation GP and the tree
+// logic (updateMapPoints / addNewMeas never read a leaf GP), so a long sequence can be mapped without paying for
+// updateGPs after every frame; train once at the end with ref3_activate + ref3_update_gps.
+void ref3_update_nogp(void* m_, float* depth, int N, const float* pose12) {
+    GPisMap3* m = (GPisMap3*)m_;
+    std::vector<float> pose(pose12, pose12 + 12);
+    if (!m->preprocData(depth, N, pose)) return;
+    if (!m->regressObs()) return;
+    m->updateMapPoints();
+    m->addNewMeas();
+    m->activeSet.clear();
+}
+// Put every non-empty cluster whose centre lies inside [lo,hi] into the active set (for ref3_update_gps).
+int ref3_activate(void* m_, const float* lo, const float* hi) {
+    GPisMap3* m = (GPisMap3*)m_;
+    if (m->t == 0) return 0;
+    std::vector<OcTree*> all;
+    m->t->QueryNonEmptyLevelC(AABB3(0.f, 0.f, 0.f, HUGE_HALF), all);
+    int n = 0;
+    for (auto q : all) {
+        Point3<float> c = q->getCenter();
+        if (c.x >= lo[0] && c.x <= hi[0] && c.y >= lo[1] && c.y <= hi[1] && c.z >= lo[2] && c.z <= hi[2]) {
+            m->activeSet.insert(q);
+            ++n;
+        }
+    }
+    return n;
+}
 int ref3_test(void* m_, float* x, int n, float* res) {
     GPisMap3* m = (GPisMap3*)m_;
     if (m->t == 0) return 0;  // the reference would dereference a null tree (GPisMap3.cpp:814)

@@ -70,6 +70,8 @@ def lib():
             "ref3_candidates": (C.c_int, [vp, f32p, C.c_float, f32p, f32p, C.c_int]),
             "ref3_insert_samples": (C.c_int, [vp, f32p, C.c_int]),
             "ref3_update_gps": (C.c_int, [vp, vp, vp]),
+            "ref3_update_nogp": (None, [vp, f32p, C.c_int, f32p]),
+            "ref3_activate": (C.c_int, [vp, f32p, f32p]),
             "ref2_create": (vp, []),
             "ref2_destroy": (None, [vp]),
             "ref2_reset": (None, [vp]),
@@ -233,15 +235,21 @@ class RefMap3(_RefMapBase):
     def set_cam(self, fx, fy, cx, cy, w, h):
         lib().ref3_set_cam(self.h, fx, fy, cx, cy, w, h)
 
-    def update(self, depth_colmajor, pose12, timed=False):
+    def update(self, depth_colmajor, pose12, timed=False, nogp=False):
         d = f32(depth_colmajor).ravel()
         p = f32(pose12)
+        if nogp:      # everything but updateGPs (the samples do not depend on the leaf GPs)
+            lib().ref3_update_nogp(self.h, d, d.size, p)
+            return
         if timed:
             ph = np.zeros(5, np.float64)
             cnt = np.zeros(2, np.int32)
             lib().ref3_update_timed(self.h, d, d.size, p, ph, cnt)
             return ph, cnt
         lib().ref3_update(self.h, d, d.size, p)
+
+    def activate(self, lo, hi):
+        return lib().ref3_activate(self.h, f32(lo), f32(hi))
 
     def update_gps(self, lo=None, hi=None):
         lo_ = f32(lo) if lo is not None else None

@@ -115,7 +115,100 @@ def seq2d_demo():
         nleaves.append(len(c))
     c, n, tr = M.clusters()
     return dict(thetas=thetas, ranges=ranges, pose6=pose6, X=X, rows=M.test(X), leaves=c, nleaves=np.array(nleaves, np.int32),
-                nsamples=np.int32(len(M.all_samples())))
+                nsamples=np.int32(len(M.all_samples())), samples=M.all_samples())
+
+
+BIGBIRD_CAMS = H.BIGBIRD_CAMS
+
+
+def seq3d():
+    """The bundled 3-D demo run (matlab/demo_gpisMap3.m:26-54: 40 masked BigBIRD depth frames, camera intrinsics
+    switched per frame with setCamera at a fixed 640x480 resolution, which exercises the stale ObsGP2D partition of
+    SURVEY.md 9-12). Inputs are stored sparsely (valid pixels only, column-major index + metres); outputs are the
+    reference's samples after frames 5, 20 and 40, its leaf count and sample count after every frame, and its result
+    rows on every 3rd point of the demo's 21x25x29 test grid."""
+    import cv2
+    base = "/root/reference/data/3D/bigbird_detergent"
+    poses = np.loadtxt(base + "/pose/poses.txt").astype(np.float32)
+    frame_nums = list(range(93, 360, 3)) + list(range(3, 91, 3))
+    cam_ids = [1, 2, 3, 4, 3, 2] * 30
+    xg, yg, zg = np.meshgrid(np.arange(-0.07, 0.1301, 0.01), np.arange(-0.1, 0.1401, 0.01), np.arange(0, 0.2801, 0.01))
+    X = np.stack([xg.ravel(order="F"), yg.ravel(order="F"), zg.ravel(order="F")], 1).astype(np.float32)[::3]
+    out = dict(X=X)
+    M = None
+    idx_all, val_all, off, cams, pose12, nleaves, nsamples = [], [], [0], [], [], [], []
+    count = 0
+    for k in range(0, len(frame_nums), 3):
+        frm, cam, row = frame_nums[k], cam_ids[count], poses[count]
+        count += 1
+        D = cv2.imread(f"{base}/masked_depth/frame{frm}_cam{cam}.png", cv2.IMREAD_UNCHANGED).astype(np.float32) * np.float32(0.0001)
+        pose = np.concatenate([row[[3, 7, 11]], row[[0, 1, 2, 4, 5, 6, 8, 9, 10]]]).astype(np.float32)
+        c = tuple(np.float32(BIGBIRD_CAMS[n][cam - 1]) for n in ("fx", "fy", "cx", "cy")) + (640, 480)
+        if M is None:
+            M = refpy.RefMap3(cam=c)
+        else:
+            M.set_cam(*c)
+        dz = np.ascontiguousarray(D.T).ravel()          # column-major, as the mex gateway hands it over
+        nz = np.flatnonzero(dz != 0).astype(np.int32)
+        idx_all.append(nz); val_all.append(dz[nz]); off.append(off[-1] + len(nz))
+        cams.append(cam); pose12.append(pose)
+        M.update(dz, pose)
+        cc, nn, tr = M.clusters()
+        nleaves.append(len(cc)); nsamples.append(len(M.all_samples()))
+        if count in (5, 20, 40):
+            out[f"samples{count}"] = M.all_samples()
+        print("seq3d frame", count, "valid", len(nz), "samples", nsamples[-1], "leaves", nleaves[-1], flush=True)
+    out.update(depth_idx=np.concatenate(idx_all), depth_val=np.concatenate(val_all), depth_off=np.array(off, np.int64),
+               cam=np.array(cams, np.int32), pose12=np.stack(pose12), nleaves=np.array(nleaves, np.int32),
+               nsamples=np.array(nsamples, np.int32), rows=M.test(X), leaves=M.clusters()[0])
+    return out
+
+
+ROOM40_LO = np.array([-0.15, -0.15, -0.15], np.float32)   # octant x,y,z >= 0 of the synthetic room + 0.15 m margin
+
+
+def room40():
+    """BASELINE configs[1]: the 40 synthetic 640x480 depth frames of the box room (gpismap_b200/synth.py) mapped by
+    the UNMODIFIED reference (every step of GPisMap3::update except updateGPs, which never changes a sample).
+    Stored: the final samples inside the room's +x+y+z octant plus a 0.15 m margin (what bench.py's reference arm and
+    cpu_baseline load, and what the GPU pipeline must reproduce bit for bit), the sample count after every frame and
+    a SHA-256 of the complete final sample array."""
+    import hashlib
+    from gpismap_b200 import synth
+    M = refpy.RefMap3()
+    ns = []
+    for k in range(40):
+        dz, pose = synth.frame(k, 40)
+        M.update(dz, pose, nogp=True)
+        ns.append(len(M.all_samples()))
+        print("room40 frame", k, "samples", ns[-1], flush=True)
+    S = M.all_samples()
+    sel = np.all(S[:, :3] >= ROOM40_LO, axis=1)
+    return dict(samples=S[sel], lo=ROOM40_LO, nsamples=np.array(ns, np.int32), total=np.int64(len(S)),
+                sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(S).tobytes()).digest(), np.uint8),
+                nleaves=np.int32(len(M.clusters()[0])))
+
+
+def map2d(seed):
+    """2-D analogue of map3d: circle samples loaded into the reference's quadtree, every leaf trained by its own
+    updateGPs, result rows of GPisMap::test_kernel (GPisMap.cpp:665-763) on random and lattice-symmetric queries."""
+    rng = np.random.default_rng(seed)
+    P = H.P2
+    s = np.concatenate([H.circle_samples(5.3, 0.35, (1.37, -0.61), rng), H.circle_samples(2.1, 0.3, (9.13, 2.27), rng)])
+    M = refpy.RefMap2()
+    M.insert_samples(s)
+    M.update_gps()
+    centres, offs, samples, trained = H.ref_map_to_csr(M, P)
+    x = np.stack([rng.uniform(-7, 13, 700), rng.uniform(-8, 7, 700)], 1).astype(np.float32)
+    g = np.arange(-6.4, 12.81, 0.8)
+    xs = np.stack(np.meshgrid(g, g - 3.2, indexing="ij"), -1).reshape(-1, 2).astype(np.float32)   # lattice planes, exact ties
+    X = np.concatenate([x, xs])
+    init = rng.uniform(size=(len(X), 6)).astype(np.float32)
+    rows = M.test(X, init.copy())
+    ncand = np.array([M.candidates(q, P["search"])[0].shape[0] for q in X], np.int32)
+    root_c, root_half = M.root()
+    return dict(samples_in=s, centres=centres, offsets=offs, samples=samples, X=X, init=init, rows=rows, ncand=ncand,
+                boxes=M.cluster_boxes(), root_c=root_c, root_half=np.float32(root_half))
 
 
 def map3d(seed):
@@ -142,6 +235,15 @@ def map3d(seed):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:   # regenerate selected fixtures: python make_golden.py seq3d map2d seq2d_demo
+        for name in only:
+            fn = {"seq3d": seq3d, "map2d": lambda: map2d(15), "seq2d_demo": seq2d_demo, "room40": room40, "seq2d": seq2d}[name]
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), **fn())
+            print(name, os.path.getsize(os.path.join(HERE, name + ".npz")))
+        sys.exit(0)
+    np.savez_compressed(os.path.join(HERE, "seq3d.npz"), **seq3d())
+    np.savez_compressed(os.path.join(HERE, "map2d.npz"), **map2d(15))
     np.savez_compressed(os.path.join(HERE, "leaf3d.npz"), **leaf(3, 24, 11))
     np.savez_compressed(os.path.join(HERE, "leaf2d.npz"), **leaf(2, 18, 12))
     np.savez_compressed(os.path.join(HERE, "obs2d.npz"), **obs2d(13))

@@ -6,6 +6,11 @@ P3 = dict(dim=3, scale=0.04, noise=5e-3, half=0.025, rtimes=2.0, search=0.025 * 
 P2 = dict(dim=2, scale=1.2, noise=1e-2, half=0.8, rtimes=4.0, search=1.2 * 4.0, var_thre=0.4)
 
 
+BIGBIRD_CAMS = dict(   # mex/mexGPisMap3.cpp:30-41 ('bigbird' table)
+    fx=[570.9361, 572.3318, 568.9403, 567.9881, 572.7638], fy=[570.9376, 572.3316, 568.9419, 567.9995, 572.7567],
+    cx=[306.8789, 309.9968, 308.4583, 310.5243, 310.4192], cy=[238.8476, 230.6296, 225.8232, 223.9443, 214.8762])
+
+
 def leaf_samples3(N, rng, spread=0.05, flat=True):
     """N samples of a gently curved surface patch inside a training ball, 9 floats each."""
     p = rng.uniform(-spread, spread, (N, 3))

@@ -95,7 +95,7 @@ def _fixture_map(cabi):
     return ctx, g, cells, P
 
 
-@pytest.mark.parametrize("version", [3, 2, 1])
+@pytest.mark.parametrize("version", [3, 1])
 def test_query_matches_reference_fixture(cabi, oracle, oracle64, version):
     """K3 + K4 against rows produced by the unmodified reference (tests/golden/map3d.npz): candidate
     counts bit-exact (incl. lattice-touching boxes), picks identical where the fixture has exact ties
@@ -142,7 +142,7 @@ def test_query_invariances(cabi):
     assert np.array_equal(ctx.query(X[perm])[np.argsort(perm)], base)
     parts = np.concatenate([ctx.query(X[:5000]), ctx.query(X[5000:5001]), ctx.query(X[5001:])])
     assert np.array_equal(parts, base)
-    # v1 (one CTA per pair) and v2 (8 queries per CTA) are different kernels: equal within tolerance only
+    # v1 (one CTA per pair) is a different kernel: equal within tolerance only
     ctx.set_eval_version(1)
     v1 = ctx.query(X)
     ev = base[:, 4] < 1.0
@@ -209,8 +209,9 @@ def test_obs_gp_matches_oracle(cabi, oracle):
     ev = g["var"] < 1e5
     assert np.array_equal(var > 1e5, ~ev)                         # same evaluated set
     assert np.array_equal(val[~ev], g["val0"][~ev])
-    assert np.abs(val[ev] - g["val"][ev]).max() / np.abs(g["val"][ev]).max() < 1e-5
-    assert np.abs(var[ev] - g["var"][ev]).max() < 2e-6
+    # K2 follows the oracle's operation order (obs_gp.cuh): bit-identical outputs
+    assert np.array_equal(val[ev], g["val"][ev])
+    assert np.array_equal(var[ev], g["var"][ev])
     s = dict(np.load(os.path.join(G, "seq2d.npz")))
     c2 = cabi.Ctx(2)
     f = (1.0 / np.sqrt(s["ranges"][0])).astype(np.float32)
@@ -218,15 +219,30 @@ def test_obs_gp_matches_oracle(cabi, oracle):
     val, var = c2.obs_test(s["obs1_xt"], 1)
     ev = s["obs1_var"] < 1e5
     assert np.array_equal(var > 1e5, ~ev)
-    assert np.abs(val[ev] - s["obs1_val"][ev]).max() / np.abs(s["obs1_val"][ev]).max() < 1e-5
-    assert np.abs(var[ev] - s["obs1_var"][ev]).max() < 2e-6
+    assert np.array_equal(val[ev], s["obs1_val"][ev])
+    assert np.array_equal(var[ev], s["obs1_var"][ev])
     ctx.close()
     c2.close()
 
 
+def _rows_report(rows, ref, dim, label):
+    """Error statistics of result rows against the reference's rows (same floors as helpers.check_rows)."""
+    w = 1 + dim
+    ev = ref[:, w] < 1.0
+    assert np.array_equal(rows[:, w] < 1.0, ev), f"{label}: evaluated mask differs"
+    ef, eg, evr = H._errs(rows[ev], ref[ev], dim)
+    rep = {"rows": int(ev.sum())}
+    for name, e, tol in (("f", ef, 1e-4), ("grad", eg, 1e-4), ("var", evr, 1e-3)):
+        rep[name] = {"median": float(np.median(e)), "p99": float(np.percentile(e, 99)), "max": float(e.max()),
+                     "within_tol": float((e < tol).mean())}
+    print(label, rep)
+    return rep
+
+
 def test_gpismap2d_end_to_end(cabi):
-    """The drop-in GPisMap on the first laser scans of the bundled sequence (stored in the fixture):
-    same leaves as the reference, same number of samples, rows within tolerance where evaluated."""
+    """The drop-in GPisMap on the first laser scans of the bundled sequence (stored in the fixture): after every
+    scan the leaves AND the samples (position, normal, value, both noises) are bit-identical to the reference's —
+    the observation GP follows the oracle's operation order — and the result rows agree within tolerance."""
     from gpismap_b200 import hostapi
     g = dict(np.load(os.path.join(G, "seq2d.npz")))
     m = hostapi.GPisMap()
@@ -235,15 +251,11 @@ def test_gpismap2d_end_to_end(cabi):
         m.update(g["thetas"], g["ranges"][i], g["pose6"][i])
         c, n = m.leaves()
         assert np.array_equal(c, g[f"leaves{i}"])                 # leaf assignment bit-exact
-        s = m.all_samples()
-        assert abs(len(s) - len(g[f"samples{i}"])) <= max(2, 0.01 * len(s))
-    rows = m.test(g["X"])
-    ref = g["rows"]
-    ev = ref[:, 3] < 1.0
-    assert np.array_equal(rows[:, 3] < 1.0, ev)
-    # the GPU observation GP rounds differently from the CPU one, so sample positions differ in the last
-    # bits and the fused field is compared loosely here; the strict checks are the leaf-level tests above
-    assert np.abs(rows[ev, 0] - ref[ev, 0]).max() < 5e-3
+        assert np.array_equal(n, g[f"leafcount{i}"])
+        assert np.array_equal(m.all_samples(), g[f"samples{i}"]), f"samples differ after scan {i}"
+    rep = _rows_report(m.test(g["X"]), g["rows"], 2, "seq2d")
+    assert rep["f"]["within_tol"] >= 0.97 and rep["f"]["p99"] < 1e-3, rep
+    assert rep["var"]["within_tol"] >= 0.97, rep
     m.close()
 
 
@@ -335,8 +347,8 @@ def test_query_on_sample_position_nan_pattern(cabi, oracle):
 
 def test_gpismap2d_whole_demo_sequence(cabi):
     """BASELINE configs[0]: all 28 scans of the reference's 2-D demo (matlab/demo_gpisMap.m) through the drop-in
-    GPisMap: the leaf count after every scan and the final leaf set equal the reference's (leaf assignment is
-    bit-exact), the evaluated mask on the demo grid is identical and f agrees where evaluated."""
+    GPisMap: the leaf count after every scan, the final leaf set and the final samples are bit-identical to the
+    reference's; the evaluated mask on the demo grid is identical and the rows agree within tolerance."""
     from gpismap_b200 import hostapi
     g = dict(np.load(os.path.join(G, "seq2d_demo.npz")))
     m = hostapi.GPisMap()
@@ -344,12 +356,79 @@ def test_gpismap2d_whole_demo_sequence(cabi):
         m.update(g["thetas"], g["ranges"][i], g["pose6"][i])
         assert m.leaves()[0].shape[0] == g["nleaves"][i], i
     assert np.array_equal(m.leaves()[0], g["leaves"])
-    s = m.all_samples()
-    assert abs(len(s) - int(g["nsamples"])) <= max(3, 0.01 * len(s))
-    rows = m.test(g["X"])
-    ref = g["rows"]
-    ev = ref[:, 3] < 1.0
-    assert np.array_equal(rows[:, 3] < 1.0, ev)
-    assert ev.sum() > 1000
-    assert np.abs(rows[ev, 0] - ref[ev, 0]).max() < 1e-2 and np.median(np.abs(rows[ev, 0] - ref[ev, 0])) < 1e-4
+    assert np.array_equal(m.all_samples(), g["samples"])
+    rep = _rows_report(m.test(g["X"]), g["rows"], 2, "seq2d_demo")
+    assert rep["rows"] > 1000
+    assert rep["f"]["within_tol"] >= 0.97 and rep["f"]["p99"] < 1e-3, rep
+    m.close()
+
+
+def test_query2d_matches_reference_fixture(cabi, oracle, oracle64):
+    """K3 + K4 in 2-D against rows produced by the unmodified reference (tests/golden/map2d.npz,
+    GPisMap::test_kernel, GPisMap.cpp:665-763): candidate counts and picks bit-exact (lattice-plane queries, exact
+    ties, > 16 candidates), rows within the stated tolerances with fp64 arbitration."""
+    g = dict(np.load(os.path.join(G, "map2d.npz")))
+    P = H.P2
+    ctx = cabi.Ctx(2)
+    pitch = 2.0 * np.float64(np.float32(P["half"]))
+    root_min = np.round((g["root_c"].astype(np.float64) - float(g["root_half"])) / pitch).astype(np.int32)
+    levels = int(round(np.log2(float(g["root_half"]) / np.float64(np.float32(P["half"])))))
+    ctx.rebase(root_min, levels)
+    cells = cabi.cells_of(g["centres"], P["half"])
+    st = ctx.leaves_update(cells, g["centres"], g["offsets"], g["samples"])
+    assert (st == 0).all()
+    ctx.leaves_set_boxes(cells, g["boxes"])
+    got, chosen, tie = ctx.query(g["X"], g["init"].copy(), debug=True)
+    assert np.array_equal(chosen[:, 0], g["ncand"])
+    offs = g["offsets"]
+    gps = [oracle.gp_train(2, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
+    gps64 = [oracle64.gp_train(2, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
+    m = oracle.make_map(2, g["centres"], P["half"], gps, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
+    m64 = oracle64.make_map(2, g["centres"], P["half"], gps64, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
+    want, ochosen, otie = m.test(g["X"], g["init"].copy(), want_choice=True)
+    want64 = m64.test(g["X"], g["init"].astype(np.float64))
+    assert np.array_equal(want, g["rows"])                      # the oracle itself reproduces the fixture
+    slot = np.array([ctx.leaf_index(c) for c in cells])
+    inv = -np.ones(slot.max() + 2, np.int64)
+    inv[slot] = np.arange(len(slot))
+    ch = chosen.copy()
+    for k in (1, 2, 3):
+        ch[:, k] = np.where(chosen[:, k] >= 0, inv[np.maximum(chosen[:, k], 0)], -1)
+    assert np.array_equal(ch, ochosen), "neighbour picks differ from the reference's std::sort order"
+    assert np.array_equal(tie, otie)
+    ev = g["ncand"] > 0
+    H.check_rows(got[ev], g["rows"][ev], want64[ev], 2, label="map2d")
+    keep = [0, 1, 2, 4, 5]
+    assert np.array_equal(got[~ev][:, keep], g["init"][~ev][:, keep])
+    ctx.close()
+
+
+def test_gpismap3_bundled_sequence(cabi):
+    """The reference's own 3-D demo run (matlab/demo_gpisMap3.m: 40 masked BigBIRD depth frames, intrinsics switched
+    per frame at a fixed resolution, which exercises the stale ObsGP2D partition of SURVEY 9-12) through the
+    drop-in GPisMap3: leaf and sample counts after every frame, the samples after frames 5, 20 and 40 and the
+    final leaf set are bit-identical to the reference's; rows on the demo grid within tolerance."""
+    from gpismap_b200 import hostapi
+    BIGBIRD_CAMS = H.BIGBIRD_CAMS
+    g = dict(np.load(os.path.join(G, "seq3d.npz")))
+    m = None
+    for k in range(len(g["cam"])):
+        cam = int(g["cam"][k])
+        c = tuple(np.float32(BIGBIRD_CAMS[n][cam - 1]) for n in ("fx", "fy", "cx", "cy")) + (640, 480)
+        if m is None:
+            m = hostapi.GPisMap3(cam=c)
+        else:
+            m.resetCam(*c)
+        dz = np.zeros(640 * 480, np.float32)
+        a, b = g["depth_off"][k], g["depth_off"][k + 1]
+        dz[g["depth_idx"][a:b]] = g["depth_val"][a:b]
+        m.update(dz, g["pose12"][k])
+        S = m.all_samples()
+        assert len(S) == g["nsamples"][k] and m.leaves()[0].shape[0] == g["nleaves"][k], (k, len(S), g["nsamples"][k])
+        if f"samples{k + 1}" in g:
+            assert np.array_equal(S, g[f"samples{k + 1}"]), f"samples differ after frame {k + 1}"
+    assert np.array_equal(m.leaves()[0], g["leaves"])
+    rep = _rows_report(m.test(g["X"]), g["rows"], 3, "seq3d")
+    assert rep["rows"] > 4000
+    assert rep["f"]["within_tol"] >= 0.97 and rep["f"]["p99"] < 1e-3, rep
     m.close()

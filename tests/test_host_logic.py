@@ -73,3 +73,28 @@ def test_tree_against_reference(ref, mocklib):
     ca, na, _ = R.clusters()
     cb, nb = M.leaves()
     assert np.array_equal(ca, cb) and np.array_equal(na, nb)
+
+
+def test_3d_bundled_sequence_bit_exact(mocklib):
+    """First frames of the reference's 3-D demo run (tests/golden/seq3d.npz) through the drop-in GPisMap3 on the
+    oracle-backed mock ABI: sample and leaf counts after every frame and the samples after frame 5 are the
+    reference's, bit for bit (preprocData, regressObs, reEvalPoints, evalPoints, tree logic; intrinsics change per
+    frame at fixed resolution: the stale ObsGP2D partition of SURVEY 9-12 is part of the contract)."""
+    from gpismap_b200 import hostapi
+    g = dict(np.load(os.path.join(G, "seq3d.npz")))
+    m = None
+    for k in range(6):
+        cam = int(g["cam"][k])
+        c = tuple(np.float32(H.BIGBIRD_CAMS[n][cam - 1]) for n in ("fx", "fy", "cx", "cy")) + (640, 480)
+        if m is None:
+            m = hostapi.GPisMap3(cam=c, libpath=mocklib)
+        else:
+            m.resetCam(*c)
+        dz = np.zeros(640 * 480, np.float32)
+        a, b = g["depth_off"][k], g["depth_off"][k + 1]
+        dz[g["depth_idx"][a:b]] = g["depth_val"][a:b]
+        m.update(dz, g["pose12"][k])
+        S = m.all_samples()
+        assert len(S) == g["nsamples"][k] and m.leaves()[0].shape[0] == g["nleaves"][k], k
+        if k + 1 == 5:
+            assert np.array_equal(S, g["samples5"])
