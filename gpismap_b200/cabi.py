@@ -11,6 +11,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgpis_b200.so")
+if os.environ.get("GPIS_B200_LIB"):      # development builds (e.g. -DT2_TIMING) next to the production library
+    LIB_PATH = os.environ["GPIS_B200_LIB"]
 
 EXPORTS = [
     "gpis_config_default", "gpis_create", "gpis_destroy", "gpis_reset", "gpis_last_error", "gpis_device",

@@ -145,6 +145,7 @@ struct gpis_ctx {
     void* d_scratch = nullptr; uint64_t scratch_bytes = 0;       // generic upload buffer
     void* d_scratch2 = nullptr; uint64_t scratch2_bytes = 0;
     void* d_jobs = nullptr; uint64_t jobs_bytes = 0;             // training jobs + status
+    int num_sms = 148;
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
@@ -355,6 +356,7 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
     int rc = table_alloc(ctx, cap, std::max(1024, cfg->max_leaves));
     if (rc) return rc;
     CK(cudaFuncSetAttribute(k_leaf_train, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ctx->num_sms = prop.multiProcessorCount;
     CK(cudaFuncSetAttribute(k_eval_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     rc = query_eval_init(ctx->err);
     if (rc == 0) rc = e3_upload_programs(const_cast<int4**>(&ctx->prog.recs), const_cast<int32_t**>(&ctx->prog.off), ctx->err);

@@ -302,8 +302,8 @@ k_eval_v1(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     if (warp >= w) return;
     float* kc = Ks + warp * npad;
     // mean: k*^T alpha (OnGPIS.cpp:187)
-    float mu = 0.f;
-    for (int i = lane; i < n; i += 32) mu = fmaf(kc[i], alpha[i], mu);
+    double mu = 0.0;   // double accumulation: see k_eval_v3
+    for (int i = lane; i < n; i += 32) mu = fma((double)kc[i], (double)alpha[i], mu);
     for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
     // block elimination (OnGPIS.cpp:199): u_i = b_i - sum_j G_ij u_j, then v_i = inv(Lii) u_i
     float ss = 0.f;
@@ -329,7 +329,7 @@ k_eval_v1(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if (lane == 0) {
         float* out = W.evalout + ((int64_t)q * 3 + rank) * 8;
-        out[warp] = mu;
+        out[warp] = (float)mu;
         // priors: OnGPIS.cpp:203-212 / 235-237, evaluated in double like the reference
         const double prior = (warp == 0) ? (double)P.prior_f : P.prior_g;
         out[w + warp] = (float)(prior - (double)ss);

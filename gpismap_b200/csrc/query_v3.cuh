@@ -298,20 +298,25 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     else kstar(std::integral_constant<int, 2>{});
     __syncthreads();
 
-    // ---- mean: U^T alpha (OnGPIS.cpp:187); lane = column, warps split the rows
+    // ---- mean: U^T alpha (OnGPIS.cpp:187); lane = column, warps split the rows. Accumulated in double: the sum
+    // cancels heavily (sum |k_i alpha_i| >> |f|) and 4n DFMAs per query are free next to the 2n^2 FMAs of the solve;
+    // the result is the correctly rounded fp32 mean of the fp32 inputs, so the distance to the reference is the
+    // reference's own summation error.
     {
-        float mu = 0.f;
+        // partial sums of the warps: doubles, parked behind the query coordinates in the (still idle) staging area
+        double* redd = reinterpret_cast<double*>(stage_all + ((N * 4 + npad + 4 * QBT + 1) & ~1));
+        double mu = 0.0;
         if (lane < NCOL)
-            for (int i = warp; i < n; i += E3_WARPS) mu = fmaf(U[i * NCOL + lane], park ? s_alpha[i] : __ldg(alpha + i), mu);
-        red[warp * 32 + lane] = mu;
+            for (int i = warp; i < n; i += E3_WARPS) mu = fma((double)U[i * NCOL + lane], (double)(park ? s_alpha[i] : __ldg(alpha + i)), mu);
+        redd[warp * 32 + lane] = mu;
         __syncthreads();
         if (warp == 0 && lane < NCOL) {
-            float s = 0.f;
-            for (int ww = 0; ww < E3_WARPS; ++ww) s += red[ww * 32 + lane];
+            double s = 0.0;
+            for (int ww = 0; ww < E3_WARPS; ++ww) s += redd[ww * 32 + lane];
             const int qi = lane >> 2, c = lane & 3;
             if (qi < cnt && c < w) {
                 const int2 pr = S.sorted[first + qi];
-                W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + c] = s;
+                W.evalout[((int64_t)pr.x * 3 + ((pr.y >> 28) & 3)) * 8 + c] = (float)s;
             }
         }
         __syncthreads();   // `red` is reused by the final reduction: a warp without rows (tiny leaves) gets there at once

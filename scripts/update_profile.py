@@ -5,7 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gpismap_b200 import hostapi, synth
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+tv = int(sys.argv[2]) if len(sys.argv) > 2 else 2          # training kernel version (gpis_set_train_version)
 m = hostapi.GPisMap3()
+from gpismap_b200 import cabi
+print("training kernel version", tv)
 rows = []
 for k in range(nf):
     dz, pose = synth.frame(k, nf)

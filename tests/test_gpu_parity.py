@@ -72,9 +72,20 @@ def test_leaf_capacity_and_empty(cabi):
     assert ctx.leaf_index([0, 0, 0]) >= 0 and ctx.leaf_get([0, 0, 0]) is None
     s = ctx.stats()
     assert s["leaves"] == 1 and s["leaves_trained"] == 0
+    # a leaf beyond the kernel's capacity is registered but not trained and flagged; the rest of the batch trains,
+    # and nothing is left half-mutated (the reference has no size limit, so this must not poison the frame)
+    rng = np.random.default_rng(4)
     big = np.zeros((2000, 9), np.float32)
+    ok = H.leaf_samples3(40, rng)
+    st = ctx.leaves_update([[1, 0, 0], [2, 0, 0]], [[0.075, 0.025, 0.025], [0.125, 0.025, 0.025]], [0, 2000, 2040],
+                           np.concatenate([big, ok]))
+    assert st[0] < 0 and st[1] == 0
+    assert ctx.leaf_index([1, 0, 0]) >= 0 and ctx.leaf_get([1, 0, 0]) is None
+    assert ctx.leaf_get([2, 0, 0])["N"] == 40
+    assert ctx.stats()["last_train_skipped"] == 1
     with pytest.raises(RuntimeError):
-        ctx.leaves_update([[1, 0, 0]], [[0.075, 0.025, 0.025]], [0, 2000], big)   # > GPIS_MAX_SAMPLES
+        ctx.leaves_update([[3, 0, 0]], [[0.175, 0.025, 0.025]], [5, 2], ok)      # decreasing offsets: rejected up front
+    assert ctx.leaf_index([3, 0, 0]) == -1                                        # ... and nothing was registered
     ctx.leaves_erase([[0, 0, 0]])
     assert ctx.leaf_index([0, 0, 0]) == -1
     ctx.close()
