@@ -19,7 +19,8 @@ EXPORTS = [
     "gpis_leaves_update", "gpis_leaves_mark", "gpis_leaves_set_boxes", "gpis_leaves_erase", "gpis_rebase", "gpis_get_rebase", "gpis_leaf_get",
     "gpis_query", "gpis_query_device", "gpis_query_debug", "gpis_leaf_index",
     "gpis_obs_train_2d", "gpis_obs_train_1d", "gpis_obs_test",
-    "gpis_export_dirty", "gpis_import", "gpis_get_stats",
+    "gpis_get_stats", "gpis_comm_unique_id", "gpis_comm_init", "gpis_replicate",
+    "gpis_snapshot_save", "gpis_snapshot_load",
 ]
 
 
@@ -43,6 +44,8 @@ class Stats(C.Structure):
         ("last_query_flops", C.c_double), ("last_query_bytes_gather", C.c_double),
         ("last_query_bytes_compulsory", C.c_double), ("last_query_ms", C.c_float), ("last_query_eval_ms", C.c_float),
         ("kernel_launches", C.c_int64), ("last_query_items", C.c_int64 * 4),
+        ("last_replicate_bytes", C.c_int64), ("last_replicate_records", C.c_int64), ("last_replicate_ms", C.c_float),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -79,10 +82,13 @@ def lib():
         L.gpis_obs_train_2d.argtypes = [vp, vp, vp, C.c_int, C.c_int]
         L.gpis_obs_train_1d.argtypes = [vp, vp, vp, C.c_int]
         L.gpis_obs_test.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
-        L.gpis_export_dirty.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
-        L.gpis_import.argtypes = [vp, vp, C.c_uint64]
         L.gpis_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.gpis_set_eval_version.argtypes = [vp, C.c_int]
+        L.gpis_comm_unique_id.argtypes = [vp]
+        L.gpis_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.gpis_replicate.argtypes = [vp, C.c_int]
+        L.gpis_snapshot_save.argtypes = [vp, C.c_char_p]
+        L.gpis_snapshot_load.argtypes = [vp, C.c_char_p]
         _lib = L
     return _lib
 
@@ -223,19 +229,31 @@ class Ctx:
         self._ck(lib().gpis_obs_test(self.h, _p(xt), d, m, _p(val), _p(var)))
         return val, var
 
-    def export_dirty(self):
-        buf = C.c_void_p()
-        nb = C.c_uint64(0)
-        self._ck(lib().gpis_export_dirty(self.h, C.byref(buf), C.byref(nb)))
-        return buf.value, nb.value
-
-    def import_records(self, ptr, nbytes):
-        self._ck(lib().gpis_import(self.h, C.c_void_p(ptr), nbytes))
-
     def stats(self):
         s = Stats()
         self._ck(lib().gpis_get_stats(self.h, C.byref(s)))
         return {k: (list(getattr(s, k)) if k == "last_query_items" else getattr(s, k)) for k, _ in Stats._fields_}
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_ubyte * 128)()
+        rc = lib().gpis_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"gpis_comm_unique_id failed ({rc}): NCCL not available")
+        return bytes(buf)
+
+    def comm_init(self, rank, world, id128):
+        buf = (C.c_ubyte * 128).from_buffer_copy(id128)
+        self._ck(lib().gpis_comm_init(self.h, rank, world, buf))
+
+    def replicate(self, root=0):
+        self._ck(lib().gpis_replicate(self.h, root))
+
+    def snapshot_save(self, path):
+        self._ck(lib().gpis_snapshot_save(self.h, os.fsencode(path)))
+
+    def snapshot_load(self, path):
+        self._ck(lib().gpis_snapshot_load(self.h, os.fsencode(path)))
 
     def set_eval_version(self, v):
         self._ck(lib().gpis_set_eval_version(self.h, v))

@@ -5,6 +5,8 @@
 #include "../../include/gpis_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (gpis_comm_init), there is no link dependency
 
 #include <algorithm>
 #include <cmath>
@@ -14,6 +16,7 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -105,6 +108,16 @@ __global__ void k_unpack_L(const float* __restrict__ tiles, int n, int nb, float
     Ld[i] = v;
 }
 
+// K5: gather / scatter of whole leaf records between the arena and one contiguous staging buffer.
+struct CopyJob { const unsigned char* src; unsigned char* dst; uint64_t bytes; };
+__global__ void __launch_bounds__(256) k_copy_records(const CopyJob* __restrict__ jobs) {
+    const CopyJob j = jobs[blockIdx.x];
+    const uint4* s = reinterpret_cast<const uint4*>(j.src);
+    uint4* d = reinterpret_cast<uint4*>(j.dst);
+    const uint64_t n16 = j.bytes >> 4;   // records are multiples of 128 bytes
+    for (uint64_t i = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.y * blockDim.x) d[i] = s[i];
+}
+
 }  // namespace gpis
 
 // ------------------------------------------------------------------ context
@@ -158,9 +171,20 @@ struct gpis_ctx {
     ObsParams op{}; bool obs_trained = false;
     int obs_ni = -1, obs_nj = -1; bool obs_repartition = true;
     std::vector<float> obs_hb0, obs_hb1; std::vector<ObsTileDesc> obs_hdesc;
-    // dirty export
-    std::vector<uint64_t> dirty_keys;
-    void* d_export = nullptr; uint64_t export_cap = 0;
+    // K5 replication (gpis_comm_init / gpis_replicate): NCCL resolved at run time
+    void* nccl_lib = nullptr;
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    ncclResult_t (*p_ncclCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*p_ncclBroadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*p_ncclCommDestroy)(ncclComm_t) = nullptr;
+    const char* (*p_ncclGetErrorString)(ncclResult_t) = nullptr;
+    std::unordered_set<uint64_t> repl_touched;   // leaves whose table entry or record changed since the last gpis_replicate
+    std::unordered_set<uint64_t> repl_trained;   // ... of which the record is new
+    std::vector<uint64_t> repl_erased;           // leaves erased since then
+    void* d_repl = nullptr; uint64_t repl_cap = 0;      // staging buffer (bounded: records travel in chunks)
+    void* d_repl_idx = nullptr; uint64_t repl_idx_cap = 0;
+    void* d_repl_jobs = nullptr; uint64_t repl_jobs_cap = 0;
     gpis_stats st{};
     int eval_version = 3;
 };
@@ -377,7 +401,9 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
     cudaFree(const_cast<int4*>(ctx->prog.recs)); cudaFree(const_cast<int32_t*>(ctx->prog.off));
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
-    cudaFree(ctx->d_export); cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_repl); cudaFree(ctx->d_repl_idx); cudaFree(ctx->d_repl_jobs);
+    if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -403,7 +429,7 @@ int gpis_reset(gpis_ctx* ctx) {
     ctx->obs_trained = false;
     ctx->obs_repartition = true;   // ObsGP2D::reset (ObsGP.cpp:198-203) runs when the map deletes gpo
     ctx->obs_ni = ctx->obs_nj = -1;
-    ctx->dirty_keys.clear();
+    ctx->repl_touched.clear(); ctx->repl_trained.clear(); ctx->repl_erased.clear();
     ctx->max_nb = 1; ctx->max_N = 1;
     derive_params(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -482,6 +508,7 @@ int gpis_leaves_mark(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const fl
         set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
         ctx->leaves[key] = hl;
         ups.push_back(make_update(key, hl));
+        ctx->repl_touched.insert(key);
     }
     return apply_updates(ctx, ups);
 }
@@ -499,6 +526,7 @@ int gpis_leaves_set_boxes(gpis_ctx* ctx, int n_leaves, const int32_t* cells, con
         for (int c = 0; c < dim; ++c) { hl.lo[c] = boxes[(size_t)i * 2 * dim + c]; hl.hi[c] = boxes[(size_t)i * 2 * dim + dim + c]; }
         hl.box_set = true;
         ups.push_back(make_update(key, hl));
+        ctx->repl_touched.insert(key);
     }
     return apply_updates(ctx, ups);
 }
@@ -519,6 +547,8 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
         ctx->free_slots.push_back(it->second.slot);
         ctx->leaves.erase(it);
         ctx->tombs++;
+        ctx->repl_touched.erase(key); ctx->repl_trained.erase(key);
+        ctx->repl_erased.push_back(key);
     }
     int rc = apply_updates(ctx, ups);
     if (rc) return rc;
@@ -619,6 +649,7 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
         HostLeaf& hl = it->second;
         set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
         if (status) status[i] = (pl.N > 0 && !pl.train) ? (int32_t)GPIS_ERR_CAPACITY : 0;
+        ctx->repl_touched.insert(key);
         if (!pl.train) {   // registered (non-empty) but not retrained
             ups.push_back(make_update(key, hl));
             continue;
@@ -658,7 +689,7 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
         if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
         hl.rec = pl.rec; hl.rec_bytes = pl.rb; hl.N = pl.N; hl.ng = pl.ng; hl.n = pl.n; hl.nb = pl.nb;
         ups.push_back(make_update(in.first, hl));
-        ctx->dirty_keys.push_back(in.first);
+        ctx->repl_trained.insert(in.first);
     }
     ctx->max_nb = std::max(ctx->max_nb, maxnb);
     ctx->max_N = std::max(ctx->max_N, maxN);
@@ -992,79 +1023,332 @@ int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, floa
     return GPIS_OK;
 }
 
-// ------------------------------------------------------------------ replication + stats
-int gpis_export_dirty(gpis_ctx* ctx, const void** buf_device, uint64_t* bytes) {
-    if (!ctx || !buf_device || !bytes) return GPIS_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
-    // de-duplicate, keep only keys that still hold a record
-    std::vector<uint64_t> keys;
-    {
-        std::unordered_map<uint64_t, int> seen;
-        for (uint64_t k : ctx->dirty_keys) {
-            auto it = ctx->leaves.find(k);
-            if (it == ctx->leaves.end() || it->second.rec == 0) continue;
-            if (seen.emplace(k, 1).second) keys.push_back(k);
-        }
+// ------------------------------------------------------------------ K5 inside the library: NCCL replication
+// One message per call: a 64-byte header, an index of table entries (every leaf whose entry or record changed on the
+// root since the last call, and the erased keys), then the new records, packed by one kernel into a bounded staging
+// buffer and broadcast chunk by chunk. Receivers allocate arena space from the index, scatter each chunk with one
+// kernel and apply all table changes at the end; nothing synchronises per record.
+struct ReplHeader { uint64_t magic, n_entries, payload_bytes; int32_t root_min[3]; int32_t levels; uint64_t pad[3]; };
+static_assert(sizeof(ReplHeader) == 64, "header is 64 bytes");
+struct ReplEntry {
+    uint64_t key, bytes, offset;      // bytes = 0: table entry only (mark / box change); offset into the record stream
+    int32_t cell[3]; int32_t erase;   // erase = 1: the leaf disappeared
+    float centre[3]; int32_t box_set;
+    float lo[3], hi[3];
+    int32_t meta[4];                  // N, ng, n, nb of the record that travels (bytes > 0)
+    int32_t pad[2];
+};
+#define GPIS_REPL_CHUNK (256ull << 20)
+
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + (ctx->p_ncclGetErrorString ? ctx->p_ncclGetErrorString(r_) : "nccl error"); \
+            return GPIS_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+static void* nccl_open(std::string& err) {
+    const char* env = std::getenv("GPIS_NCCL_LIB");
+    // dlopen by soname returns the copy the process already holds (e.g. the one torch loaded), else the system one
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        if (void* h = dlopen(n, RTLD_NOW | RTLD_LOCAL)) return h;
     }
-    uint64_t total = 0;
-    for (uint64_t k : keys) total += align_up(ctx->leaves[k].rec_bytes, 256);
-    int rc = ensure(ctx, &ctx->d_export, &ctx->export_cap, std::max<uint64_t>(total, 256));
-    if (rc) return rc;
-    uint64_t off = 0;
-    for (uint64_t k : keys) {
-        const HostLeaf& hl = ctx->leaves[k];
-        CK(cudaMemcpyAsync((unsigned char*)ctx->d_export + off, (const void*)hl.rec, hl.rec_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        // the candidate box may have been overridden after training (gpis_leaves_set_boxes): ship the current one
-        float box[8] = {hl.lo[0], hl.lo[1], hl.lo[2], 0.f, hl.hi[0], hl.hi[1], hl.hi[2], 0.f};
-        CK(cudaMemcpyAsync((unsigned char*)ctx->d_export + off + offsetof(LeafHeader, lo), box, sizeof(box), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // `box` is a stack buffer
-        off += align_up(hl.rec_bytes, 256);
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->dirty_keys.clear();
-    *buf_device = ctx->d_export;
-    *bytes = total;
+    err = std::string("NCCL not found: ") + (dlerror() ? dlerror() : "dlopen failed");
+    return nullptr;
+}
+
+int gpis_comm_unique_id(void* id128) {
+    if (!id128) return GPIS_ERR_ARG;
+    std::string err;
+    void* h = nccl_open(err);
+    if (!h) return GPIS_ERR_STATE;
+    auto fn = (ncclResult_t(*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+    if (!fn) return GPIS_ERR_STATE;
+    ncclUniqueId id;
+    if (fn(&id) != ncclSuccess) return GPIS_ERR_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id128, &id, 128);
     return GPIS_OK;
 }
 
-int gpis_import(gpis_ctx* ctx, const void* buf_device, uint64_t bytes) {
-    if (!ctx || (bytes && !buf_device)) return GPIS_ERR_ARG;
+int gpis_comm_init(gpis_ctx* ctx, int rank, int world, const void* id128) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
-    const int dim = ctx->cfg.dim;
+    if (!ctx->nccl_lib) ctx->nccl_lib = nccl_open(ctx->err);
+    if (!ctx->nccl_lib) return GPIS_ERR_STATE;
+    ctx->p_ncclCommInitRank = (decltype(ctx->p_ncclCommInitRank))dlsym(ctx->nccl_lib, "ncclCommInitRank");
+    ctx->p_ncclBroadcast = (decltype(ctx->p_ncclBroadcast))dlsym(ctx->nccl_lib, "ncclBroadcast");
+    ctx->p_ncclCommDestroy = (decltype(ctx->p_ncclCommDestroy))dlsym(ctx->nccl_lib, "ncclCommDestroy");
+    ctx->p_ncclGetErrorString = (decltype(ctx->p_ncclGetErrorString))dlsym(ctx->nccl_lib, "ncclGetErrorString");
+    if (!ctx->p_ncclCommInitRank || !ctx->p_ncclBroadcast || !ctx->p_ncclCommDestroy) { ctx->err = "NCCL symbols missing"; return GPIS_ERR_STATE; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    if (ctx->comm) { ctx->p_ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    NCK(ctx->p_ncclCommInitRank(&ctx->comm, world, id, rank));
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    return GPIS_OK;
+}
+
+static int erase_one(gpis_ctx* ctx, uint64_t key, std::vector<SlotUpdate>& ups) {
+    auto it = ctx->leaves.find(key);
+    if (it == ctx->leaves.end()) return 0;
+    SlotUpdate u{};
+    u.key = key; u.slot = it->second.slot; u.live = 0;
+    ups.push_back(u);
+    if (it->second.rec) arena_free(ctx, it->second.rec, it->second.rec_bytes);
+    ctx->free_slots.push_back(it->second.slot);
+    ctx->leaves.erase(it);
+    ctx->tombs++;
+    return 1;
+}
+
+}  // extern "C" (templates below)
+
+// The sender's half of a message: index of table entries (+ record sizes / stream offsets) and the header.
+// full = every leaf of the table (snapshot); otherwise what changed since the last gpis_replicate.
+static void build_message(gpis_ctx* ctx, bool full, ReplHeader& hd, std::vector<ReplEntry>& idx) {
+    idx.clear();
+    hd = ReplHeader{};
+    if (!full)
+        for (uint64_t k : ctx->repl_erased) { ReplEntry e{}; e.key = k; e.erase = 1; idx.push_back(e); }
     uint64_t off = 0;
+    auto add = [&](uint64_t k, const HostLeaf& hl, bool with_record) {
+        ReplEntry e{};
+        e.key = k;
+        for (int c = 0; c < 3; ++c) { e.cell[c] = hl.cell[c]; e.centre[c] = hl.centre[c]; e.lo[c] = hl.lo[c]; e.hi[c] = hl.hi[c]; }
+        e.box_set = hl.box_set ? 1 : 0;
+        if (with_record && hl.rec) {
+            e.bytes = hl.rec_bytes; e.offset = off; off += align_up(hl.rec_bytes, 256);
+            e.meta[0] = hl.N; e.meta[1] = hl.ng; e.meta[2] = hl.n; e.meta[3] = hl.nb;
+        }
+        idx.push_back(e);
+    };
+    if (full) {
+        std::vector<uint64_t> keys;
+        for (auto& kv : ctx->leaves) keys.push_back(kv.first);
+        std::sort(keys.begin(), keys.end());   // deterministic files
+        for (uint64_t k : keys) add(k, ctx->leaves[k], true);
+    } else {
+        for (uint64_t k : ctx->repl_touched) {
+            auto it = ctx->leaves.find(k);
+            if (it != ctx->leaves.end()) add(k, it->second, ctx->repl_trained.count(k) != 0);
+        }
+    }
+    hd.magic = 0x4750495352455031ull; hd.n_entries = idx.size(); hd.payload_bytes = off;
+    for (int c = 0; c < 3; ++c) hd.root_min[c] = ctx->qp.root_min[c];
+    hd.levels = ctx->qp.levels;
+}
+
+// Moves the record stream of a message through the bounded staging buffer, chunk by chunk. On the sending side the
+// chunk is gathered from the arena by one kernel and handed to `xfer` (NCCL broadcast, or a copy to a file); on the
+// receiving side `xfer` fills the staging buffer and one kernel scatters it to the freshly reserved records.
+template <class Xfer>
+static int stream_records(gpis_ctx* ctx, bool sender, const ReplHeader& hd, const std::vector<ReplEntry>& idx,
+                          const std::vector<uint64_t>& new_rec, Xfer&& xfer) {
+    if (!hd.payload_bytes) return 0;
+    uint64_t biggest = 0;
+    for (const ReplEntry& e : idx) biggest = std::max<uint64_t>(biggest, align_up(e.bytes, 256));
+    const uint64_t chunk_cap = std::max<uint64_t>(GPIS_REPL_CHUNK, biggest);
+    int rc = ensure(ctx, &ctx->d_repl, &ctx->repl_cap, std::min<uint64_t>(chunk_cap, hd.payload_bytes));
+    if (rc) return rc;
+    std::vector<CopyJob> jobs;
+    size_t i = 0;
+    while (i < idx.size()) {
+        jobs.clear();
+        uint64_t base = 0, used = 0;
+        bool have = false;
+        size_t j = i;
+        for (; j < idx.size(); ++j) {   // maximal run of travelling records that fits the staging buffer
+            const ReplEntry& e = idx[j];
+            if (e.erase || !e.bytes) continue;
+            const uint64_t sz = align_up(e.bytes, 256);
+            if (!have) { base = e.offset; have = true; }
+            if (used + sz > chunk_cap && used > 0) break;
+            unsigned char* stage = (unsigned char*)ctx->d_repl + (e.offset - base);
+            if (sender) jobs.push_back(CopyJob{(const unsigned char*)ctx->leaves[e.key].rec, stage, e.bytes});
+            else jobs.push_back(CopyJob{stage, (unsigned char*)new_rec[j], e.bytes});
+            used += sz;
+        }
+        i = j;
+        if (!have) break;
+        rc = ensure(ctx, &ctx->d_repl_jobs, &ctx->repl_jobs_cap, jobs.size() * sizeof(CopyJob));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->d_repl_jobs, jobs.data(), jobs.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
+        if (sender) { k_copy_records<<<dim3((unsigned)jobs.size(), 16), 256, 0, ctx->stream>>>((const CopyJob*)ctx->d_repl_jobs); ctx->st.kernel_launches++; }
+        rc = xfer(used);
+        if (rc) return rc;
+        if (!sender) { k_copy_records<<<dim3((unsigned)jobs.size(), 16), 256, 0, ctx->stream>>>((const CopyJob*)ctx->d_repl_jobs); ctx->st.kernel_launches++; }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// Receiver, before the records arrive: erases, table capacity, arena space for every travelling record.
+static int receive_prepare(gpis_ctx* ctx, const std::vector<ReplEntry>& idx, std::vector<uint64_t>& new_rec) {
+    std::vector<SlotUpdate> ups;
+    for (const ReplEntry& e : idx) if (e.erase) erase_one(ctx, e.key, ups);
+    int rc = apply_updates(ctx, ups);
+    if (rc) return rc;
+    rc = table_reserve(ctx, (int)idx.size());
+    if (rc) return rc;
+    new_rec.assign(idx.size(), 0);
+    for (size_t i = 0; i < idx.size(); ++i)
+        if (!idx[i].erase && idx[i].bytes) {
+            rc = arena_alloc(ctx, idx[i].bytes, &new_rec[i]);
+            if (rc) { for (size_t k = 0; k < i; ++k) if (new_rec[k]) arena_free(ctx, new_rec[k], idx[k].bytes); return rc; }
+        }
+    return 0;
+}
+// Receiver, after the scatter kernels (stream order): install the table entries, release replaced records.
+static int receive_install(gpis_ctx* ctx, const ReplHeader& hd, const std::vector<ReplEntry>& idx, const std::vector<uint64_t>& new_rec) {
     std::vector<SlotUpdate> ups;
     std::vector<std::pair<uint64_t, uint64_t>> to_free;
-    while (off + sizeof(LeafHeader) <= bytes) {
-        LeafHeader h;
-        CK(cudaMemcpy(&h, (const unsigned char*)buf_device + off, sizeof(h), cudaMemcpyDeviceToHost));
-        if (h.bytes == 0 || off + h.bytes > bytes) break;
-        int rc = table_reserve(ctx, 1);
-        if (rc) return rc;
-        auto it = ctx->leaves.find(h.key);
+    for (size_t i = 0; i < idx.size(); ++i) {
+        const ReplEntry& e = idx[i];
+        if (e.erase) continue;
+        auto it = ctx->leaves.find(e.key);
         if (it == ctx->leaves.end()) {
             HostLeaf hl{};
             hl.slot = take_slot(ctx);
-            it = ctx->leaves.emplace(h.key, hl).first;
+            it = ctx->leaves.emplace(e.key, hl).first;
         }
         HostLeaf& hl = it->second;
-        uint64_t rec = 0;
-        rc = arena_alloc(ctx, h.bytes, &rec);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync((void*)rec, (const unsigned char*)buf_device + off, h.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
-        hl.rec = rec; hl.rec_bytes = h.bytes; hl.N = h.N; hl.ng = h.ng; hl.n = h.n; hl.nb = h.nb;
-        set_geometry(ctx, hl, h.cell, h.centre);
-        for (int c = 0; c < 3; ++c) { hl.lo[c] = h.lo[c]; hl.hi[c] = h.hi[c]; }
-        hl.box_set = true;
-        ctx->max_nb = std::max(ctx->max_nb, h.nb);
-        ctx->max_N = std::max(ctx->max_N, h.N);
-        ups.push_back(make_update(h.key, hl));
-        off += align_up(h.bytes, 256);
+        for (int c = 0; c < 3; ++c) { hl.cell[c] = e.cell[c]; hl.centre[c] = e.centre[c]; hl.lo[c] = e.lo[c]; hl.hi[c] = e.hi[c]; }
+        hl.box_set = e.box_set != 0;
+        if (e.bytes) {
+            if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
+            hl.rec = new_rec[i]; hl.rec_bytes = e.bytes;
+            hl.N = e.meta[0]; hl.ng = e.meta[1]; hl.n = e.meta[2]; hl.nb = e.meta[3];
+            ctx->max_nb = std::max(ctx->max_nb, hl.nb);
+            ctx->max_N = std::max(ctx->max_N, hl.N);
+        }
+        ups.push_back(make_update(e.key, hl));
     }
     int rc = apply_updates(ctx, ups);
     if (rc) return rc;
     for (auto& f : to_free) arena_free(ctx, f.first, f.second);
+    for (int c = 0; c < 3; ++c) ctx->qp.root_min[c] = hd.root_min[c];
+    ctx->qp.levels = hd.levels;
+    return 0;
+}
+
+extern "C" {
+
+int gpis_replicate(gpis_ctx* ctx, int root) {
+    if (!ctx) return GPIS_ERR_ARG;
+    if (!ctx->comm) { ctx->err = "gpis_replicate before gpis_comm_init"; return GPIS_ERR_STATE; }
+    if (root < 0 || root >= ctx->comm_world) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const bool is_root = ctx->comm_rank == root;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    std::vector<ReplEntry> idx;
+    ReplHeader hd{};
+    if (is_root) build_message(ctx, false, hd, idx);
+    int rc = ensure(ctx, &ctx->d_repl_idx, &ctx->repl_idx_cap, 256);
+    if (rc) return rc;
+    if (is_root) CK(cudaMemcpyAsync(ctx->d_repl_idx, &hd, sizeof(hd), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ctx->p_ncclBroadcast(ctx->d_repl_idx, ctx->d_repl_idx, sizeof(hd), ncclUint8, root, ctx->comm, ctx->stream));
+    if (!is_root) {
+        CK(cudaMemcpyAsync(&hd, ctx->d_repl_idx, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (hd.magic != 0x4750495352455031ull) { ctx->err = "gpis_replicate: bad header"; return GPIS_ERR_STATE; }
+        idx.resize(hd.n_entries);
+    }
+    const uint64_t idx_bytes = hd.n_entries * sizeof(ReplEntry);
+    if (hd.n_entries) {
+        rc = ensure(ctx, &ctx->d_repl_idx, &ctx->repl_idx_cap, idx_bytes);
+        if (rc) return rc;
+        if (is_root) CK(cudaMemcpyAsync(ctx->d_repl_idx, idx.data(), idx_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        NCK(ctx->p_ncclBroadcast(ctx->d_repl_idx, ctx->d_repl_idx, idx_bytes, ncclUint8, root, ctx->comm, ctx->stream));
+        if (!is_root) {
+            CK(cudaMemcpyAsync(idx.data(), ctx->d_repl_idx, idx_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    std::vector<uint64_t> new_rec;
+    if (!is_root) { rc = receive_prepare(ctx, idx, new_rec); if (rc) return rc; }
+    rc = stream_records(ctx, is_root, hd, idx, new_rec, [&](uint64_t used) -> int {
+        NCK(ctx->p_ncclBroadcast(ctx->d_repl, ctx->d_repl, used, ncclUint8, root, ctx->comm, ctx->stream));
+        return 0;
+    });
+    if (rc) return rc;
+    if (!is_root) { rc = receive_install(ctx, hd, idx, new_rec); if (rc) return rc; }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->st.last_replicate_ms = ms;
+    ctx->st.last_replicate_bytes = (int64_t)(hd.payload_bytes + idx_bytes + sizeof(hd));
+    ctx->st.last_replicate_records = 0;
+    for (const ReplEntry& e : idx) ctx->st.last_replicate_records += (e.bytes ? 1 : 0);
+    if (is_root) { ctx->repl_touched.clear(); ctx->repl_trained.clear(); ctx->repl_erased.clear(); }
     return GPIS_OK;
+}
+
+// ------------------------------------------------------------------ snapshot
+// The same message as gpis_replicate with every leaf in it, written to / read from a flat file:
+//   [ReplHeader 64 B][gpis_config][n_entries x ReplEntry][record stream, 256-byte aligned records]
+// The reference has no persistence (its map dies with the process, GPisMap3.cpp:951-972 only lists points); this
+// gives the trained device map checkpoint/resume and a wire format a replica can be started from.
+int gpis_snapshot_save(gpis_ctx* ctx, const char* path) {
+    if (!ctx || !path) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) { ctx->err = std::string("cannot open ") + path; return GPIS_ERR_ARG; }
+    ReplHeader hd{};
+    std::vector<ReplEntry> idx;
+    build_message(ctx, true, hd, idx);
+    bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1 && std::fwrite(&ctx->cfg, sizeof(ctx->cfg), 1, f) == 1 &&
+              (idx.empty() || std::fwrite(idx.data(), sizeof(ReplEntry), idx.size(), f) == idx.size());
+    std::vector<unsigned char> host;
+    int rc = 0;
+    if (ok) rc = stream_records(ctx, true, hd, idx, std::vector<uint64_t>(), [&](uint64_t used) -> int {
+        host.resize(used);
+        CK(cudaMemcpyAsync(host.data(), ctx->d_repl, used, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (std::fwrite(host.data(), 1, used, f) != used) { ctx->err = "short write"; return GPIS_ERR_ARG; }
+        return 0;
+    });
+    std::fclose(f);
+    if (!ok) { ctx->err = "short write"; return GPIS_ERR_ARG; }
+    return rc;
+}
+
+int gpis_snapshot_load(gpis_ctx* ctx, const char* path) {
+    if (!ctx || !path) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    std::FILE* f = std::fopen(path, "rb");
+    if (!f) { ctx->err = std::string("cannot open ") + path; return GPIS_ERR_ARG; }
+    ReplHeader hd{};
+    gpis_config cfg{};
+    std::vector<ReplEntry> idx;
+    bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && hd.magic == 0x4750495352455031ull && std::fread(&cfg, sizeof(cfg), 1, f) == 1;
+    if (ok && (cfg.dim != ctx->cfg.dim || cfg.map_scale != ctx->cfg.map_scale || cfg.cluster_half != ctx->cfg.cluster_half)) {
+        std::fclose(f);
+        ctx->err = "snapshot was written with different map parameters (dim / map_scale / cluster_half)";
+        return GPIS_ERR_ARG;
+    }
+    if (ok) { idx.resize(hd.n_entries); ok = idx.empty() || std::fread(idx.data(), sizeof(ReplEntry), idx.size(), f) == idx.size(); }
+    if (!ok) { std::fclose(f); ctx->err = "not a gpis snapshot (or truncated)"; return GPIS_ERR_ARG; }
+    int rc = gpis_reset(ctx);
+    std::vector<uint64_t> new_rec;
+    if (!rc) rc = receive_prepare(ctx, idx, new_rec);
+    std::vector<unsigned char> host;
+    if (!rc) rc = stream_records(ctx, false, hd, idx, new_rec, [&](uint64_t used) -> int {
+        host.resize(used);
+        if (std::fread(host.data(), 1, used, f) != used) { ctx->err = "truncated snapshot"; return GPIS_ERR_ARG; }
+        CK(cudaMemcpyAsync(ctx->d_repl, host.data(), used, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `host` is reused by the next chunk
+        return 0;
+    });
+    std::fclose(f);
+    if (!rc) rc = receive_install(ctx, hd, idx, new_rec);
+    if (!rc) CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
 }
 
 int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out) {

@@ -471,6 +471,7 @@ int GPisMap::insertSamples(const float* s, int n) {
     if (!d->ensure_ctx()) return 0;
     return d->core.insert_samples(s, n);
 }
+int GPisMap::activateAll() { return d->core.activate_all(); }
 int GPisMap::trainActive() {
     if (!d->ensure_ctx()) return 0;
     const int n = (int)d->core.active.size();

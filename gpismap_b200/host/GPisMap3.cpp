@@ -636,6 +636,7 @@ int GPisMap3::insertSamples(const float* s, int n) {
     if (!d->ensure_ctx()) return 0;
     return d->core.insert_samples(s, n);
 }
+int GPisMap3::activateAll() { return d->core.activate_all(); }
 int GPisMap3::trainActive() {
     if (!d->ensure_ctx()) return 0;
     const int n = (int)d->core.active.size();

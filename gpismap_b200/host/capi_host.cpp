@@ -55,6 +55,7 @@ int gm3_leaves(void* m, float* centres, int* counts, int cap) {
 }
 int gm3_insert_samples(void* m, const float* s, int n) { return ((GPisMap3*)m)->insertSamples(s, n); }
 int gm3_train_active(void* m) { return ((GPisMap3*)m)->trainActive(); }
+int gm3_activate_all(void* m) { return ((GPisMap3*)m)->activateAll(); }
 // development aid: coarse host profile (map_core.hpp), read and reset
 void gm_profile(double* secs16, long long* calls16) {
     for (int i = 0; i < 16; ++i) { secs16[i] = gpismap_host::g_prof_s[i]; calls16[i] = gpismap_host::g_prof_n[i]; gpismap_host::g_prof_s[i] = 0; gpismap_host::g_prof_n[i] = 0; }
@@ -102,6 +103,7 @@ int gm2_leaves(void* m, float* centres, int* counts, int cap) {
 }
 int gm2_insert_samples(void* m, const float* s, int n) { return ((GPisMap*)m)->insertSamples(s, n); }
 int gm2_train_active(void* m) { return ((GPisMap*)m)->trainActive(); }
+int gm2_activate_all(void* m) { return ((GPisMap*)m)->activateAll(); }
 void gm2_timing(void* m, double* phases5, int* counts3, float* train_ms) {
     const GPisMapTiming& t = ((GPisMap*)m)->lastTiming();
     for (int i = 0; i < 5; ++i) phases5[i] = t.phase[i];

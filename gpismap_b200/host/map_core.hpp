@@ -110,6 +110,16 @@ public:
     void activate(const std::vector<int>& touched) {
         for (int c : touched) active.insert(LeafHandle{c, tree->cell(c).gen});
     }
+    // every non-empty leaf becomes active: the next train_active() retrains the whole map on its current samples
+    int activate_all() {
+        if (!tree) return 0;
+        std::vector<int> all;
+        float zero[D];
+        for (int a = 0; a < D; ++a) zero[a] = 0.f;
+        tree->query_clusters(zero, 1.0e6f, all);
+        for (int c : all) active.insert(LeafHandle{c, tree->cell(c).gen});
+        return (int)all.size();
+    }
     void drop_freed(const std::vector<int>& freed) {
         for (int c : freed) {
             // gen was bumped when the cell was freed; the stale handle carries gen-1

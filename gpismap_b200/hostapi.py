@@ -31,6 +31,7 @@ def lib(path=None):
             getattr(L, pfx + "_leaves").argtypes = [vp, vp, vp, i]
             getattr(L, pfx + "_insert_samples").argtypes = [vp, vp, i]
             getattr(L, pfx + "_train_active").argtypes = [vp]
+            getattr(L, pfx + "_activate_all").argtypes = [vp]
             getattr(L, pfx + "_timing").argtypes = [vp, vp, vp, vp]
             getattr(L, pfx + "_ctx").argtypes = [vp]
             getattr(L, pfx + "_ctx").restype = vp
@@ -105,6 +106,10 @@ class _MapBase:
 
     def train_active(self):
         return self._fn("train_active")(self.h)
+
+    def activate_all(self):
+        """Mark every non-empty leaf dirty; the next train_active() retrains the whole map on its current samples."""
+        return self._fn("activate_all")(self.h)
 
     def timing(self):
         ph = np.zeros(5, np.float64)

@@ -157,11 +157,28 @@ int gpis_obs_train_1d(gpis_ctx* ctx, const float* theta, const float* f, int n);
  *   reference would not evaluate, val is untouched and var = 1e6. */
 int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val_inout, float* var_inout);
 
-/* ---------------------------------------------------------------- replication (K5) and stats
- * Device-resident packed copy of every record trained since the last call (what a replica needs
- * after an update); consumed by gpis_import on the other ranks after an NCCL all-gather. */
-int gpis_export_dirty(gpis_ctx* ctx, const void** buf_device, uint64_t* bytes);
-int gpis_import(gpis_ctx* ctx, const void* buf_device, uint64_t bytes);
+/* ---------------------------------------------------------------- replication (K5), snapshot and stats */
+/* K5 inside the library. The trained leaf table is replicated over NCCL (NVLink / NVSwitch) so that query batches can
+ * be sharded over GPUs; the query path itself has no collective.
+ *   gpis_comm_unique_id  rank 0 calls it and hands the 128 bytes to the other ranks by any host channel
+ *                        (ncclGetUniqueId); NCCL is resolved at run time, preferring the copy already in the process.
+ *   gpis_comm_init       every rank, once per context (ncclCommInitRank).
+ *   gpis_replicate       collective: every rank calls it after the root's update. The root ships everything that
+ *                        changed since its previous call — new records (packed by one kernel, broadcast in bounded
+ *                        chunks), table-only changes (leaves registered without a GP, effective boxes), erased
+ *                        leaves, the root box — and the other ranks install it: afterwards they answer queries
+ *                        bit-identically to the root. No per-record synchronisation. */
+int gpis_comm_unique_id(void* id128);
+int gpis_comm_init(gpis_ctx* ctx, int rank, int world, const void* id128);
+int gpis_replicate(gpis_ctx* ctx, int root);
+
+/* Snapshot of the trained device map: the message gpis_replicate ships, with every leaf in it, as a
+ * flat file — [64-byte header][gpis_config][index of table entries][256-byte aligned leaf records]. The reference has
+ * no persistence (GPisMap3.cpp:951-972 only lists sample positions). gpis_snapshot_load resets the context first and
+ * refuses a file written with a different dim / map_scale / cluster_half. Queries after a load are bit-identical to
+ * queries before the save. The host-side tree is not part of it (a loaded map answers test(), it cannot be updated). */
+int gpis_snapshot_save(gpis_ctx* ctx, const char* path);
+int gpis_snapshot_load(gpis_ctx* ctx, const char* path);
 
 typedef struct gpis_stats {
     int64_t leaves;            /* leaves registered in the table */
@@ -184,6 +201,10 @@ typedef struct gpis_stats {
     int64_t kernel_launches;   /* kernels of this library launched since gpis_create */
     /* last gpis_query*: evaluation CTAs launched with 8, 6, 4 and 1 queries per CTA (batch fill = evals / capacity) */
     int64_t last_query_items[4];
+    /* last gpis_replicate on this rank */
+    int64_t last_replicate_bytes, last_replicate_records;
+    float last_replicate_ms;   /* CUDA-event time on this rank's stream: pack, broadcasts, scatter, table apply */
+    int32_t reserved1;
 } gpis_stats;
 int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out);
 

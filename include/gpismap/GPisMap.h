@@ -59,6 +59,7 @@ public:
     void getAllPoints(std::vector<float>& pos);
     int insertSamples(const float* samples7, int n);
     int trainActive();
+    int activateAll();                          // mark every non-empty leaf dirty (retrain the whole map with trainActive)
     int numLeaves();
     void getLeaves(std::vector<float>& centres, std::vector<int>& counts);
     void getAllSamples(std::vector<float>& samples7);

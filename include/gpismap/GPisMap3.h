@@ -67,6 +67,7 @@ public:
     // test hooks mirroring oracle/ref_harness.cpp: bulk-load samples (9 floats each) and train
     int insertSamples(const float* samples9, int n);
     int trainActive();
+    int activateAll();                          // mark every non-empty leaf dirty (retrain the whole map with trainActive)
     int numLeaves();
     void getLeaves(std::vector<float>& centres, std::vector<int>& counts);
     void getAllSamples(std::vector<float>& samples9);

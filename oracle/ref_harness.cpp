@@ -291,6 +291,65 @@ int ref3_activate(void* m_, const float* lo, const float* hi) {
     }
     return n;
 }
+// ---- exact tree snapshot. The final state of a mapped octree cannot be rebuilt by re-inserting its samples (the
+// minimum-spacing rule, octree.cpp:331-333, rejects pairs that ended up closer than that across cell boundaries), so
+// long runs are frozen as a pre-order dump and rebuilt node by node with the reference's own Subdivide().
+//   flags: one byte per visited node, bit 0 = leaf, bit 1 = holds a sample (its 9 floats follow in `samples`).
+// Subtrees whose box does not touch [lo,hi] are recorded as empty leaves. Returns the node count; sample count in *ns.
+namespace {
+void dump_rec(OcTree* t, const float* lo, const float* hi, std::vector<unsigned char>& flags, std::vector<float>& smp) {
+    Point3<float> c = t->getCenter();
+    const float h = t->getHalfLength();
+    const bool touch = !(c.x + h < lo[0] || c.x - h > hi[0] || c.y + h < lo[1] || c.y - h > hi[1] || c.z + h < lo[2] || c.z - h > hi[2]);
+    if (!touch) { flags.push_back(1); return; }
+    unsigned char f = (t->leaf ? 1 : 0) | (t->node != nullptr ? 2 : 0);
+    flags.push_back(f);
+    if (t->node != nullptr) { float s[9]; Samples3::dump(t->node, s); smp.insert(smp.end(), s, s + 9); }
+    if (!t->leaf) {
+        OcTree* ch[8] = {t->northWestFront, t->northEastFront, t->southWestFront, t->southEastFront,
+                         t->northWestBack, t->northEastBack, t->southWestBack, t->southEastBack};
+        for (int i = 0; i < 8; ++i) dump_rec(ch[i], lo, hi, flags, smp);
+    }
+}
+int load_rec(OcTree* t, const unsigned char* flags, size_t& fi, const float* smp, size_t& si) {
+    const unsigned char f = flags[fi++];
+    int cnt = 0;
+    if (f & 2) { t->node = Samples3::make(smp + 9 * si); ++si; cnt = 1; }
+    if (!(f & 1)) {
+        t->Subdivide();
+        t->leaf = false;
+        OcTree* ch[8] = {t->northWestFront, t->northEastFront, t->southWestFront, t->southEastFront,
+                         t->northWestBack, t->northEastBack, t->southWestBack, t->southEastBack};
+        for (int i = 0; i < 8; ++i) cnt += load_rec(ch[i], flags, fi, smp, si);
+    }
+    t->numNodes = cnt;
+    return cnt;
+}
+}  // namespace
+int ref3_tree_dump(void* m_, const float* lo, const float* hi, unsigned char* flags, int cap_flags, float* samples,
+                   int cap_samples, float* root_c_half, int* ns) {
+    GPisMap3* m = (GPisMap3*)m_;
+    if (m->t == 0) return 0;
+    std::vector<unsigned char> f;
+    std::vector<float> s;
+    dump_rec(m->t, lo, hi, f, s);
+    Point3<float> c = m->t->getCenter();
+    root_c_half[0] = c.x; root_c_half[1] = c.y; root_c_half[2] = c.z; root_c_half[3] = m->t->getHalfLength();
+    *ns = (int)(s.size() / 9);
+    if ((int)f.size() <= cap_flags && *ns <= cap_samples) {
+        std::memcpy(flags, f.data(), f.size());
+        std::memcpy(samples, s.data(), s.size() * sizeof(float));
+    }
+    return (int)f.size();
+}
+int ref3_tree_load(void* m_, const unsigned char* flags, int nflags, const float* samples, int ns, const float* root_c_half) {
+    GPisMap3* m = (GPisMap3*)m_;
+    m->reset();
+    m->t = new OcTree(AABB3(Point3<float>(root_c_half[0], root_c_half[1], root_c_half[2]), root_c_half[3]), (OcTree*)0);
+    size_t fi = 0, si = 0;
+    const int cnt = load_rec(m->t, flags, fi, samples, si);
+    return (fi == (size_t)nflags && si == (size_t)ns) ? cnt : -1;
+}
 int ref3_test(void* m_, float* x, int n, float* res) {
     GPisMap3* m = (GPisMap3*)m_;
     if (m->t == 0) return 0;  // the reference would dereference a null tree (GPisMap3.cpp:814)

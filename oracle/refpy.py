@@ -72,6 +72,8 @@ def lib():
             "ref3_update_gps": (C.c_int, [vp, vp, vp]),
             "ref3_update_nogp": (None, [vp, f32p, C.c_int, f32p]),
             "ref3_activate": (C.c_int, [vp, f32p, f32p]),
+            "ref3_tree_dump": (C.c_int, [vp, f32p, f32p, vp, C.c_int, f32p, C.c_int, f32p, i32p]),
+            "ref3_tree_load": (C.c_int, [vp, vp, C.c_int, f32p, C.c_int, f32p]),
             "ref2_create": (vp, []),
             "ref2_destroy": (None, [vp]),
             "ref2_reset": (None, [vp]),
@@ -247,6 +249,25 @@ class RefMap3(_RefMapBase):
             lib().ref3_update_timed(self.h, d, d.size, p, ph, cnt)
             return ph, cnt
         lib().ref3_update(self.h, d, d.size, p)
+
+    def tree_dump(self, lo, hi):
+        """Pre-order snapshot of the octree restricted to the box [lo,hi]: (flags uint8, samples (ns, 9), root [cx,cy,cz,half])."""
+        lo, hi = f32(lo), f32(hi)
+        root = np.zeros(4, np.float32)
+        ns = np.zeros(1, np.int32)
+        nf = lib().ref3_tree_dump(self.h, lo, hi, None, 0, np.zeros(9, np.float32), 0, root, ns)
+        flags = np.zeros(max(nf, 1), np.uint8)
+        smp = np.zeros((max(int(ns[0]), 1), 9), np.float32)
+        lib().ref3_tree_dump(self.h, lo, hi, flags.ctypes.data_as(C.c_void_p), nf, smp, int(ns[0]), root, ns)
+        return flags[:nf], smp[:int(ns[0])], root
+
+    def tree_load(self, flags, samples, root):
+        flags = np.ascontiguousarray(flags, np.uint8)
+        smp = f32(samples)
+        n = lib().ref3_tree_load(self.h, flags.ctypes.data_as(C.c_void_p), flags.size, smp, smp.shape[0], f32(root))
+        if n < 0:
+            raise ValueError("tree snapshot is inconsistent")
+        return n
 
     def activate(self, lo, hi):
         return lib().ref3_activate(self.h, f32(lo), f32(hi))

@@ -174,9 +174,10 @@ ROOM40_HI = np.array([9.0, 0.95, 0.95], np.float32)
 def room40():
     """BASELINE configs[1]: the 40 synthetic 640x480 depth frames of the box room (gpismap_b200/synth.py) mapped by
     the UNMODIFIED reference (every step of GPisMap3::update except updateGPs, which never changes a sample).
-    Stored: the final samples around a patch of the +x wall (what bench.py's reference arm and cpu_baseline load, and
-    what the GPU pipeline must reproduce bit for bit), the sample count after every frame and a SHA-256 of the
-    complete final sample array (508,149 samples in 5,316 leaves)."""
+    Stored: an exact pre-order snapshot of the reference's octree around a patch of the +x wall (refpy.tree_dump:
+    re-inserting the samples cannot rebuild the tree, the minimum-spacing rule would drop ~18 % of them) — what
+    bench.py's reference arm and cpu_baseline load, and what the GPU pipeline must reproduce bit for bit —, the sample
+    count after every frame and a SHA-256 of the complete final sample array (508,149 samples in 5,316 leaves)."""
     import hashlib
     from gpismap_b200 import synth
     M = refpy.RefMap3()
@@ -187,9 +188,9 @@ def room40():
         ns.append(len(M.all_samples()))
         print("room40 frame", k, "samples", ns[-1], flush=True)
     S = M.all_samples()
-    sel = np.all((S[:, :3] >= ROOM40_LO) & (S[:, :3] <= ROOM40_HI), axis=1)
-    return dict(samples=S[sel], lo=ROOM40_LO, hi=ROOM40_HI, nsamples=np.array(ns, np.int32), total=np.int64(len(S)),
-                sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(S).tobytes()).digest(), np.uint8),
+    flags, smp, root = M.tree_dump(ROOM40_LO, ROOM40_HI)
+    return dict(tree_flags=flags, samples=smp, root=root, lo=ROOM40_LO, hi=ROOM40_HI, nsamples=np.array(ns, np.int32),
+                total=np.int64(len(S)), sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(S).tobytes()).digest(), np.uint8),
                 nleaves=np.int32(len(M.clusters()[0])))
 
 

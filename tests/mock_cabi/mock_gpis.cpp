@@ -188,14 +188,17 @@ int gpis_obs_test(gpis_ctx* c, const float* xt, int d, int m, float* val, float*
     gpo_obs_test(c->obs, xt, m, val, var);
     return GPIS_OK;
 }
-int gpis_export_dirty(gpis_ctx*, const void**, uint64_t*) { return GPIS_ERR_STATE; }
-int gpis_import(gpis_ctx*, const void*, uint64_t) { return GPIS_ERR_STATE; }
 int gpis_get_stats(gpis_ctx* c, gpis_stats* out) {
     c->st.leaves = (int64_t)c->leaves.size();
     *out = c->st;
     return GPIS_OK;
 }
 int gpis_set_eval_version(gpis_ctx*, int) { return GPIS_OK; }
+int gpis_comm_unique_id(void*) { return GPIS_ERR_STATE; }
+int gpis_comm_init(gpis_ctx*, int, int, const void*) { return GPIS_ERR_STATE; }
+int gpis_replicate(gpis_ctx*, int) { return GPIS_ERR_STATE; }
+int gpis_snapshot_save(gpis_ctx*, const char*) { return GPIS_ERR_STATE; }
+int gpis_snapshot_load(gpis_ctx*, const char*) { return GPIS_ERR_STATE; }
 int gpis_debug_program(int, int, int32_t*, int) { return -1; }
 
 }  // extern "C"
