@@ -390,7 +390,7 @@ def main():
         dist.destroy_process_group()
 
 
-def arbitrate(got, ref32, ref64, dim=3):
+def arbitrate(got, ref32, ref64, dim=3, explain=None):
     """check_rows semantics (tests/helpers.py) as a report: a row is *pinned* for a quantity when the fp32 reference is
     within half the tolerance of the fp64 evaluation of the same formulas; pinned rows must match the reference within
     the tolerance (1e-4 on f and grad f, 1e-3 on the variances), the others must be no further from fp64 than 4x the
@@ -422,7 +422,7 @@ def fp64_shadow(M, P_lo, P_hi, rows_x):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as H
     P = H.P3
-    O, O64 = oraclepy.Oracle(), oraclepy.Oracle(double=True)
+    O, O64 = oraclepy.Oracle(), oraclepy.Oracle(double=True, cov_float=True)
     centres, nsamp, trained = M.clusters()
     boxes = M.cluster_boxes()
     need = np.all((centres > P_lo - 0.1001) & (centres < P_hi + 0.1001), axis=1)
@@ -435,9 +435,11 @@ def fp64_shadow(M, P_lo, P_hi, rows_x):
     m64 = O64.make_map(3, centres[idx], P["half"], g64, P["search"], P["var_thre"], P["noise"], boxes=boxes[idx])
     chunks = np.array_split(np.arange(len(rows_x)), max(1, min(len(rows_x) // 64, 4 * (os.cpu_count() or 8))))
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 8) as ex:
-        w32 = np.concatenate(list(ex.map(lambda c: m32.test(rows_x[c]), chunks)))
+        r32 = list(ex.map(lambda c: m32.test(rows_x[c], want_choice=True), chunks))
         w64 = np.concatenate(list(ex.map(lambda c: m64.test(rows_x[c]), chunks)))
-    return w32, w64, len(idx)
+    w32 = np.concatenate([r[0] for r in r32])
+    chosen = np.concatenate([r[1] for r in r32])
+    return w32, w64, len(idx), chosen, g64
 
 
 def cpu_baseline(args, gmap, X):
@@ -480,13 +482,17 @@ def cpu_baseline(args, gmap, X):
             if getattr(args, "parity_rows", 0):
                 cut = np.flatnonzero(inner)[getattr(args, "parity_rows"):]
                 inner[cut] = False
-            w32, w64, nl = fp64_shadow(M, P_lo, P_hi, qs[inner])
+            w32, w64, nl, chosen, g64 = fp64_shadow(M, P_lo, P_hi, qs[inner])
             sel = inner & both
             sub = both[inner]
+            xin, chin = qs[inner][sub], chosen[sub]
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers as H
             parity = {"gpu_map_samples_sha256_equals_reference_map": same, "gpu_map_samples": int(len(S)),
                       "evaluated_mask_identical": bool(np.array_equal(res[:, 4] < 1.0, got[:, 4] < 1.0)),
                       "oracle_fp32_equals_reference_rows": bool(np.array_equal(w32[sub], res[sel])),
-                      "fp64_arbitration": arbitrate(got[sel], res[sel], w64[sub]),
+                      "fp64_arbitration": arbitrate(got[sel], res[sel], w64[sub],
+                                                    explain=lambda i: H.selection_ambiguity(g64, chin[i], xin[i], H.P3["var_thre"], 3)),
                       "fp64_leaves": nl,
                       "all_rows": _plain_report(got[both], res[both]),
                       "note": "GPU map retrained on its final samples (activateAll + trainActive) vs the reference's own updateGPs + test on "

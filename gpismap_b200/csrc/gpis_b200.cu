@@ -323,6 +323,8 @@ static void derive_params(gpis_ctx* ctx) {
     t.scale = c.map_scale;
     t.a = (float)(std::sqrt(3.0) / (double)c.map_scale);               // covFnc.cpp:147
     t.a2 = t.a * t.a;
+    t.refine = 1;
+    if (const char* e = std::getenv("GPIS_REFINE")) t.refine = std::atoi(e) ? 1 : 0;   // development switch (profiles/r02_history.md)
     ObsParams& o = ctx->op;
     o.a = 1 / c.obs_scale;                                             // covFnc.cpp:51
     o.diag = (float)(1.0 + (double)c.obs_noise);                       // covFnc.cpp:57

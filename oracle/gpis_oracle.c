@@ -15,19 +15,30 @@
 
 int gpo_real_bytes(void) { return (int)sizeof(real); }
 
+/* Scalar type of the covariance ENTRIES. Normally the build's `real`. With -DCOV_FLOAT (libgpisoracle64r.so: REAL=double,
+ * COV_FLOAT) every entry of K and k* is evaluated and rounded exactly as in the fp32 build and only the linear algebra
+ * (Cholesky, solves, dot products, fusion) runs in double: "the reference's algorithm in exact arithmetic on the
+ * reference's own float covariance entries". That is the arbiter for what fp32 pins: against it, the fp32 reference's
+ * distance is its own linear-algebra rounding error, not the (common) rounding of the covariance entries. */
+#ifdef COV_FLOAT
+typedef float creal;
+#else
+typedef real creal;
+#endif
 /* ------------------------------------------------------------------ a1: covFnc.cpp:29-33 */
-static real kf(real r, real a) { return (real)((1.0 + (double)(a * r)) * exp((double)(-a * r))); }
-static real kf1(real r, real dx, real a) { return (real)((double)(a * a * dx) * exp((double)(-a * r))); }
-static real kf2(real r, real dx1, real dx2, real delta, real a) {
-    return (real)((double)(a * a * (delta - a * dx1 * dx2 / r)) * exp((double)(-a * r)));
+static real kf(creal r, creal a) { return (real)(creal)((1.0 + (double)(a * r)) * exp((double)(-a * r))); }
+static real kf1(creal r, creal dx, creal a) { return (real)(creal)((double)(a * a * dx) * exp((double)(-a * r))); }
+static real kf2(creal r, creal dx1, creal dx2, creal delta, creal a) {
+    return (real)(creal)((double)(a * a * (delta - a * dx1 * dx2 / r)) * exp((double)(-a * r)));
 }
 static real sqrt_real(real v) { return sizeof(real) == 4 ? (real)sqrtf((float)v) : (real)sqrt((double)v); }
 /* (x1.col(k)-x2.col(j)).norm(): sequential sum of squares, then sqrt in the scalar type */
-static real dist(const real* a, const real* b, int dim) {
-    real s = 0;
-    for (int c = 0; c < dim; ++c) { real d = a[c] - b[c]; s += d * d; }
-    return sqrt_real(s);
+static creal dist(const real* a, const real* b, int dim) {
+    creal s = 0;
+    for (int c = 0; c < dim; ++c) { creal d = (creal)a[c] - (creal)b[c]; s += d * d; }
+    return sizeof(creal) == 4 ? (creal)sqrtf((float)s) : (creal)sqrt((double)s);
 }
+#define CDIFF(p, q) ((creal)(p) - (creal)(q))
 
 /* ------------------------------------------------------------------ a2: train covariance
  * covFnc.cpp:142-256 (3D), 317-402 (2D). gradidx[k] = compacted index or -1
@@ -35,35 +46,35 @@ static real dist(const real* a, const real* b, int dim) {
 static void matern_train_core(int dim, const real* x, const int* gradidx, int N, int ng, real scale,
                               const real* sigx, const real* siggrad, real* K) {
     const int n = N + dim * ng;
-    const real a = (real)(sqrt(3.0) / (double)scale); /* covFnc.cpp:147 */
-    const real a2 = a * a;
+    const creal a = (creal)(sqrt(3.0) / (double)scale); /* covFnc.cpp:147 */
+    const creal a2 = a * a;
     memset(K, 0, sizeof(real) * (size_t)n * n);
 #define KK(i, j) K[(size_t)(i) * n + (j)]
     for (int k = 0; k < N; ++k) {
         const int gk = gradidx[k];
         for (int j = k; j < N; ++j) {
             if (k == j) {
-                KK(k, k) = (real)(1.0 + (double)sigx[k]); /* :173 */
+                KK(k, k) = (real)(creal)(1.0 + (double)sigx[k]); /* :173 */
                 if (gk >= 0) {
                     for (int c = 0; c < dim; ++c) {
                         const int kc = N + c * ng + gk;
                         if (dim == 2 && c == 0) /* 2D quirk, covFnc.cpp:352 */
-                            KK(kc, kc) = (real)((double)a2 + sqrt((double)(sigx[k] * siggrad[k])));
+                            KK(kc, kc) = (real)(creal)((double)a2 + sqrt((double)((creal)sigx[k] * (creal)siggrad[k])));
                         else
-                            KK(kc, kc) = a2 + siggrad[k]; /* :182,186,190 / :355 */
+                            KK(kc, kc) = (real)(creal)(a2 + (creal)siggrad[k]); /* :182,186,190 / :355 */
                     }
                 }
                 continue;
             }
             const real* xk = x + (size_t)k * dim;
             const real* xj = x + (size_t)j * dim;
-            const real r = dist(xk, xj, dim);
+            const creal r = dist(xk, xj, dim);
             const int gj = gradidx[j];
             KK(k, j) = KK(j, k) = kf(r, a); /* :194-195 */
             if (gk >= 0) {
                 for (int c = 0; c < dim; ++c) { /* :198-203 */
                     const int kc = N + c * ng + gk;
-                    const real v = -kf1(r, xk[c] - xj[c], a);
+                    const real v = -kf1(r, CDIFF(xk[c], xj[c]), a);
                     KK(kc, j) = KK(j, kc) = v;
                 }
                 if (gj >= 0) {
@@ -76,7 +87,7 @@ static void matern_train_core(int dim, const real* x, const int* gradidx, int N,
                         for (int e = c; e < dim; ++e) {
                             const int kc = N + c * ng + gk, ke = N + e * ng + gk;
                             const int jc = N + c * ng + gj, je = N + e * ng + gj;
-                            const real v = kf2(r, xk[c] - xj[c], xk[e] - xj[e], c == e ? (real)1 : (real)0, a);
+                            const real v = kf2(r, CDIFF(xk[c], xj[c]), CDIFF(xk[e], xj[e]), c == e ? (creal)1 : (creal)0, a);
                             KK(kc, je) = KK(je, kc) = v;
                             if (e != c) KK(ke, jc) = KK(jc, ke) = v;
                         }
@@ -84,7 +95,7 @@ static void matern_train_core(int dim, const real* x, const int* gradidx, int N,
             } else if (gj >= 0) { /* :239-249 */
                 for (int c = 0; c < dim; ++c) {
                     const int jc = N + c * ng + gj;
-                    const real v = kf1(r, xk[c] - xj[c], a);
+                    const real v = kf1(r, CDIFF(xk[c], xj[c]), a);
                     KK(k, jc) = KK(jc, k) = v;
                 }
             }
@@ -115,14 +126,14 @@ int gpo_matern_train(int dim, const float* x, const float* gradflag, int N, floa
 int gpo_matern_test(int dim, const real* x, const int* gradidx, int N, int ng, const real* xt, real scale,
                     real* Ks) {
     const int n = N + dim * ng, w = 1 + dim;
-    const real a = (real)(sqrt(3.0) / (double)scale);
+    const creal a = (creal)(sqrt(3.0) / (double)scale);
     memset(Ks, 0, sizeof(real) * (size_t)n * w);
     for (int k = 0; k < N; ++k) {
         const real* xk = x + (size_t)k * dim;
-        const real r = dist(xk, xt, dim);
+        const creal r = dist(xk, xt, dim);
         real* row = Ks + (size_t)k * w;
         row[0] = kf(r, a);
-        for (int c = 0; c < dim; ++c) row[1 + c] = kf1(r, xk[c] - xt[c], a);
+        for (int c = 0; c < dim; ++c) row[1 + c] = kf1(r, CDIFF(xk[c], xt[c]), a);
         const int gk = gradidx[k];
         if (gk >= 0) {
             for (int c = 0; c < dim; ++c) {
@@ -131,7 +142,7 @@ int gpo_matern_test(int dim, const real* x, const int* gradidx, int N, int ng, c
                 for (int e = 0; e < dim; ++e) {
                     /* the reference evaluates the upper triangle and copies it down */
                     const int c0 = c < e ? c : e, e0 = c < e ? e : c;
-                    rc[1 + e] = kf2(r, xk[c0] - xt[c0], xk[e0] - xt[e0], c == e ? (real)1 : (real)0, a);
+                    rc[1 + e] = kf2(r, CDIFF(xk[c0], xt[c0]), CDIFF(xk[e0], xt[e0]), c == e ? (creal)1 : (creal)0, a);
                 }
             }
         }

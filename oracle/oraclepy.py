@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 def build(force=False):
     """Compile the C restatement (and, when /root/reference is present, oracle/_ref)."""
     need = force or not all(
-        os.path.exists(os.path.join(_HERE, f)) for f in ("libgpisoracle.so", "libgpisoracle64.so")
+        os.path.exists(os.path.join(_HERE, f)) for f in ("libgpisoracle.so", "libgpisoracle64.so", "libgpisoracle64r.so")
     )
     if need:
         subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"] + (["-B"] if force else []))
@@ -23,8 +23,11 @@ def build(force=False):
 
 
 class Oracle:
-    def __init__(self, double=False):
-        name = "libgpisoracle64.so" if double else "libgpisoracle.so"
+    def __init__(self, double=False, cov_float=False):
+        """double: linear algebra (and, unless cov_float, the covariance entries) in fp64. cov_float (with double): the
+        covariance entries are evaluated and rounded exactly as in the fp32 build, only the linear algebra is fp64 —
+        the arbiter of the parity tests (gpis_oracle.c, COV_FLOAT)."""
+        name = ("libgpisoracle64r.so" if cov_float else "libgpisoracle64.so") if double else "libgpisoracle.so"
         path = os.path.join(_HERE, name)
         if not os.path.exists(path):
             build()

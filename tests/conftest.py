@@ -27,6 +27,14 @@ def oracle64():
 
 
 @pytest.fixture(scope="session")
+def oracle64r():
+    """fp64 linear algebra on the fp32 build's covariance entries: the arbiter of what fp32 pins."""
+    from oracle import oraclepy
+    oraclepy.build()
+    return oraclepy.Oracle(double=True, cov_float=True)
+
+
+@pytest.fixture(scope="session")
 def ref():
     """The unmodified reference built into oracle/_ref (skips when it was never built)."""
     from oracle import oraclepy, refpy

@@ -412,7 +412,7 @@ def test_gpismap2d_whole_demo_sequence(cabi):
     m.close()
 
 
-def test_query2d_matches_reference_fixture(cabi, oracle, oracle64):
+def test_query2d_matches_reference_fixture(cabi, oracle, oracle64r):
     """K3 + K4 in 2-D against rows produced by the unmodified reference (tests/golden/map2d.npz,
     GPisMap::test_kernel, GPisMap.cpp:665-763): candidate counts and picks bit-exact (lattice-plane queries, exact
     ties, > 16 candidates), rows within the stated tolerances with fp64 arbitration."""
@@ -431,9 +431,9 @@ def test_query2d_matches_reference_fixture(cabi, oracle, oracle64):
     assert np.array_equal(chosen[:, 0], g["ncand"])
     offs = g["offsets"]
     gps = [oracle.gp_train(2, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
-    gps64 = [oracle64.gp_train(2, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
+    gps64 = [oracle64r.gp_train(2, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
     m = oracle.make_map(2, g["centres"], P["half"], gps, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
-    m64 = oracle64.make_map(2, g["centres"], P["half"], gps64, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
+    m64 = oracle64r.make_map(2, g["centres"], P["half"], gps64, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
     want, ochosen, otie = m.test(g["X"], g["init"].copy(), want_choice=True)
     want64 = m64.test(g["X"], g["init"].astype(np.float64))
     assert np.array_equal(want, g["rows"])                      # the oracle itself reproduces the fixture
@@ -446,7 +446,10 @@ def test_query2d_matches_reference_fixture(cabi, oracle, oracle64):
     assert np.array_equal(ch, ochosen), "neighbour picks differ from the reference's std::sort order"
     assert np.array_equal(tie, otie)
     ev = g["ncand"] > 0
-    H.check_rows(got[ev], g["rows"][ev], want64[ev], 2, label="map2d")
+    evi = np.flatnonzero(ev)
+    rep = H.check_rows(got[ev], g["rows"][ev], want64[ev], 2, label="map2d",
+                       explain=lambda i: H.selection_ambiguity(gps64, ochosen[evi[i]], g["X"][evi[i]], P["var_thre"], 2))
+    print("map2d", rep)
     keep = [0, 1, 2, 4, 5]
     assert np.array_equal(got[~ev][:, keep], g["init"][~ev][:, keep])
     ctx.close()
