@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--noise-mm", type=float, default=1.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rtimes", type=float, default=2.0,
+                    help="training-ball radius multiple (reference macro GPISMAP3_RTIMES = 2; BASELINE configs[4] raises the points per leaf: 2.5)")
     return ap.parse_args()
 
 
@@ -146,8 +148,8 @@ def run_reference(args, rank, world):
     if not refpy.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpisref.so was not built (needs /root/reference at build time)"}))
         return
-    if args.frames != 40 or abs(args.noise_mm - 1.0) > 1e-9:
-        print(json.dumps({"impl": "reference", "unavailable": "the frozen reference map exists for --frames 40 --noise-mm 1 only"}))
+    if args.frames != 40 or abs(args.noise_mm - 1.0) > 1e-9 or args.rtimes != 2.0:
+        print(json.dumps({"impl": "reference", "unavailable": "the frozen reference map exists for --frames 40 --noise-mm 1 --rtimes 2 only"}))
         return
     cores = refpy.lib().ref_hardware_concurrency()
     M, ntrain, t_train, g = load_region_reference(refpy)
@@ -184,7 +186,7 @@ def run_reference(args, rank, world):
 def workload_config(args):
     return {"workload": f"3D SDF query: {args.grid}^3 grid (f, grad f, variance) against a GPisMap3 map trained from "
                         f"{args.frames} synthetic 640x480 depth frames of the box room (BASELINE configs[2] on configs[1])",
-            "grid": args.grid, "frames": args.frames, "depth_noise_mm_at_1m": args.noise_mm,
+            "grid": args.grid, "frames": args.frames, "depth_noise_mm_at_1m": args.noise_mm, "rtimes": args.rtimes,
             "l2": "inputs larger than L2 (query + result arrays 0.7 GB, leaf records tens of GB)",
             "sharding": "z-planes round-robin over ranks, trained leaf records broadcast over NCCL"}
 
@@ -218,7 +220,7 @@ def main():
     update_ms, train_ms, repl_ms, repl_mb = [], [], [], []
     gmap = None
     if rank == 0:
-        gmap = hostapi.GPisMap3(device=local)
+        gmap = hostapi.GPisMap3(device=local, rtimes=(args.rtimes if args.rtimes != 2.0 else 0.0))
         ctx = cabi.Ctx(3, local, borrowed=gmap.ctx_handle())
     else:
         ctx = cabi.Ctx(3, local)
@@ -234,6 +236,7 @@ def main():
             update_ms.append(1e3 * (time.perf_counter() - t0))
             train_ms.append(gmap.timing()[2])
         if world > 1:
+            dist.barrier()      # replication time must not include waiting for rank 0's update
             ctx.replicate(0)
             st_r = ctx.stats()
             repl_ms.append(st_r["last_replicate_ms"])
@@ -454,9 +457,9 @@ def cpu_baseline(args, gmap, X):
         oraclepy.build()
         if not refpy.available():
             return {"value": None, "unit": "queries/s", "cores": None, "kind": "reference", "sample": "oracle/_ref not built"}
-        if args.frames != 40 or abs(args.noise_mm - 1.0) > 1e-9:
+        if args.frames != 40 or abs(args.noise_mm - 1.0) > 1e-9 or getattr(args, "rtimes", 2.0) != 2.0:
             return {"value": None, "unit": "queries/s", "cores": None, "kind": "reference",
-                    "sample": "the frozen reference map exists for --frames 40 --noise-mm 1 only"}
+                    "sample": "the frozen reference map exists for --frames 40 --noise-mm 1 --rtimes 2 only"}
         cores = refpy.lib().ref_hardware_concurrency()
         M, ntrain, t_train, g = load_region_reference(refpy)
         q = region_queries(args.grid)

@@ -133,7 +133,7 @@ class Ctx:
 
     def close(self):
         if getattr(self, "h", None):
-            if not self.borrowed:
+            if not self.borrowed and lib is not None:      # `lib` is gone during interpreter shutdown
                 lib().gpis_destroy(self.h)
             self.h = None
 

@@ -42,6 +42,7 @@ struct GPisMap3::Impl {
     camParam cam;
     MapCore<3> core;
     GPisMap3Timing timing{};
+    GPisMap3Tuning tuning{};
     float u_obs_limit[2] = {0.f, 0.f}, v_obs_limit[2] = {0.f, 0.f};
     std::vector<float> vu_grid;
     std::vector<float> obs_valid_u, obs_valid_v, obs_zinv, obs_valid_xyzlocal, obs_valid_xyzglobal;
@@ -62,6 +63,8 @@ struct GPisMap3::Impl {
         gpis_config_default(&cfg, 3);
         cfg.map_scale = setting.map_scale_param;
         cfg.map_noise = setting.map_noise_param;
+        cfg.cluster_half = tuning.tree_cluster_half;
+        cfg.search_half = tuning.tree_cluster_half * 3.0;      // GPisMap3.cpp:811  C_leng*3.0
         return core.ensure_ctx(cfg);
     }
 
@@ -592,6 +595,13 @@ void GPisMap3::resetCam(camParam c) {   // GPisMap3.cpp:117-123
     d->vu_grid.clear();
 }
 void GPisMap3::setDevice(int dev) { d->core.device_ = dev; }
+bool GPisMap3::setTuning(const GPisMap3Tuning& t) {
+    if (d->core.tree || d->core.ctx) return false;   // the constants are baked into the tree and the device context
+    d->tuning = t;
+    d->core.tparam = TreeParam(t.tree_min_half, t.tree_max_half, t.tree_init_root_half, t.tree_cluster_half, 1e-6f, false);
+    d->core.rtimes_ = t.rtimes;
+    return true;
+}
 const GPisMap3Timing& GPisMap3::lastTiming() const { return d->timing; }
 void* GPisMap3::cabiContext() { d->ensure_ctx(); return d->core.ctx; }
 

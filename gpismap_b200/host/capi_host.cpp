@@ -19,6 +19,15 @@ void* gm3_create_cam(int device, float fx, float fy, float cx, float cy, int w, 
     m->setDevice(device);
     return m;
 }
+int gm3_set_tuning(void* m, float rtimes, float min_half, float max_half, float init_root_half, float cluster_half) {
+    GPisMap3Tuning t;
+    if (rtimes > 0) t.rtimes = rtimes;
+    if (min_half > 0) t.tree_min_half = min_half;
+    if (max_half > 0) t.tree_max_half = max_half;
+    if (init_root_half > 0) t.tree_init_root_half = init_root_half;
+    if (cluster_half > 0) t.tree_cluster_half = cluster_half;
+    return ((GPisMap3*)m)->setTuning(t) ? 1 : 0;
+}
 void gm3_destroy(void* m) { delete (GPisMap3*)m; }
 void gm3_reset(void* m) { ((GPisMap3*)m)->reset(); }
 void gm3_set_cam(void* m, float fx, float fy, float cx, float cy, int w, int h) {

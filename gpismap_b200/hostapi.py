@@ -38,6 +38,7 @@ def lib(path=None):
         L.gm3_create_cam.restype = vp
         L.gm3_create_cam.argtypes = [i, f, f, f, f, i, i]
         L.gm3_set_cam.argtypes = [vp, f, f, f, f, i, i]
+        L.gm3_set_tuning.argtypes = [vp, f, f, f, f, f]
         L.gm3_update.argtypes = [vp, vp, i, vp]
         L.gm2_update.argtypes = [vp, vp, vp, i, vp]
         _libs[path] = L
@@ -126,9 +127,15 @@ class GPisMap3(_MapBase):
     dim = 3
     pfx = "gm3"
 
-    def __init__(self, device=0, cam=None, libpath=None):
+    def __init__(self, device=0, cam=None, libpath=None, rtimes=0.0, tree_min_half=0.0, tree_max_half=0.0,
+                 tree_init_root_half=0.0, tree_cluster_half=0.0):
+        """The tree / training-ball constants (reference: compile-time macros, params.h:40-44) default to the
+        reference's values; pass e.g. rtimes=2.5 for BASELINE configs[4]'s larger leaves."""
         self.L = lib(libpath)
         self.h = self.L.gm3_create(device) if cam is None else self.L.gm3_create_cam(device, *cam)
+        if rtimes or tree_min_half or tree_max_half or tree_init_root_half or tree_cluster_half:
+            if not self.L.gm3_set_tuning(self.h, rtimes, tree_min_half, tree_max_half, tree_init_root_half, tree_cluster_half):
+                raise RuntimeError("setTuning refused")
 
     def resetCam(self, fx, fy, cx, cy, w, h):
         self.L.gm3_set_cam(self.h, fx, fy, cx, cy, w, h)

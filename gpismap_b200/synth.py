@@ -72,6 +72,39 @@ def frame(k, nframes, noise_mm=1.0, seed=0):
     return depth_colmajor(depth_frame(t, R, noise_mm=noise_mm, rng=rng)), pose12(t, R)
 
 
+_WALK = {}
+
+
+def walk_pose(k, nframes=1000, seed=1):
+    """Pose k of a bounded random-walk trajectory (BASELINE configs[3], SURVEY.md 8d: 1000 frames, seed 1): position,
+    yaw and pitch do a reflected random walk inside the room; deterministic for (nframes, seed)."""
+    key = (nframes, seed)
+    if key not in _WALK:
+        rng = np.random.default_rng(seed)
+        lim = np.array([0.9, 0.7, 0.5])
+        p = np.zeros(3); yaw = 0.123; pitch = 0.0
+        out = []
+        for _ in range(nframes):
+            p = p + rng.normal(0, 0.03, 3)
+            p = np.where(np.abs(p) > lim, np.sign(p) * (2 * lim - np.abs(p)), p)
+            yaw += rng.normal(0.02, 0.05)
+            pitch = float(np.clip(pitch + rng.normal(0, 0.03), -0.6, 0.6))
+            out.append((p.copy(), yaw, pitch))
+        _WALK[key] = out
+    p, yaw, pitch = _WALK[key][k]
+    fwd = np.array([np.cos(yaw) * np.cos(pitch), np.sin(yaw) * np.cos(pitch), np.sin(pitch)])
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0]))
+    right /= np.linalg.norm(right)
+    down = np.cross(fwd, right)
+    return p, np.stack([right, down, fwd], 1)
+
+
+def walk_frame(k, nframes=1000, noise_mm=1.0, seed=1):
+    t, R = walk_pose(k, nframes, seed)
+    rng = np.random.default_rng(seed * 100003 + 7919 * k + 13)
+    return depth_colmajor(depth_frame(t, R, noise_mm=noise_mm, rng=rng)), pose12(t, R)
+
+
 def query_grid(n, lo=ROOM_LO, hi=ROOM_HI, inflate=0.1, z_slab=None):
     """n^3 points (or an [z0, z1) slab of them) over the inflated room box, interleaved xyz float32."""
     a = lo - inflate

@@ -34,6 +34,21 @@ typedef struct GPisMap3Param_ {   // cpp/include/GPisMap3.h:48-81
           map_scale_param((float)gpismap_defaults::kMapScale3), map_noise_param((float)gpismap_defaults::kMapNoise3) {}
 } GPisMap3Param;
 
+// Tree / training-ball constants that the reference fixes at compile time (cpp/include/params.h:40-44,
+// cpp/src/GPisMap3.cpp:26-31); here they are run-time values so that BASELINE configs[3]/[4] (larger leaves, larger
+// maps) need no rebuild. Defaults reproduce the reference. Not part of the reference API: see setTuning().
+struct GPisMap3Tuning {
+    float rtimes;                 // training-ball radius = rtimes * cluster half  (GPISMAP3_RTIMES)
+    float tree_min_half;          // GPISMAP3_TREE_MIN_HALF_LENGTH
+    float tree_max_half;          // GPISMAP3_TREE_MAX_HALF_LENGTH
+    float tree_init_root_half;    // GPISMAP3_TREE_INIT_ROOT_HALF_LENGTH
+    float tree_cluster_half;      // GPISMAP3_TREE_CLUSTER_HALF_LENGTH (the query's search box is 3x this, GPisMap3.cpp:811)
+    GPisMap3Tuning()
+        : rtimes((float)gpismap_defaults::kRtimes3), tree_min_half((float)gpismap_defaults::kTree3MinHalf),
+          tree_max_half((float)gpismap_defaults::kTree3MaxHalf), tree_init_root_half((float)gpismap_defaults::kTree3InitRootHalf),
+          tree_cluster_half((float)gpismap_defaults::kTree3ClusterHalf) {}
+};
+
 // Per-phase wall-clock of the last update() call, seconds (preproc, regressObs, updateMapPoints,
 // addNewMeas, updateGPs) — the phases of GPisMap3::update (cpp/src/GPisMap3.cpp:218-237).
 struct GPisMap3Timing {
@@ -62,6 +77,7 @@ public:
 
     // ---- additions (not in the reference API)
     void setDevice(int cuda_device);            // before the first update(); default 0
+    bool setTuning(const GPisMap3Tuning& t);    // before the first update() / after reset(); false once a map exists
     const GPisMap3Timing& lastTiming() const;
     void* cabiContext();                        // the gpis_ctx* underneath (tests / benches)
     // test hooks mirroring oracle/ref_harness.cpp: bulk-load samples (9 floats each) and train

@@ -17,17 +17,31 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 
-def available():
-    return os.path.exists(_PATH)
+def available(variant=None):
+    return os.path.exists(_path_of(variant))
+
+
+def _path_of(variant):
+    return _PATH if not variant else os.path.join(_HERE, "_ref", f"libgpisref_{variant}.so")
 
 
 _lib = None
+_variant = None
+
+
+def use_variant(variant):
+    """Switch to a variant build of the reference (oracle/Makefile: params_variants/<variant>/params.h override, e.g.
+    "rtimes25"); None = the default build. Objects created before the switch keep working with their own library."""
+    global _lib, _variant
+    if variant != _variant:
+        _variant = variant
+        _lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(_PATH)
+        L = C.CDLL(_path_of(_variant))
         vp = C.c_void_p
         sig = {
             "ref_hardware_concurrency": (C.c_int, []),

@@ -28,6 +28,7 @@ for k in range(nf):
     if rank == 0:
         dz, pose = synth.frame(k, 40)
         gmap.update(dz, pose)
+    dist.barrier()          # the timing below must not include waiting for rank 0's update
     ctx.replicate(0)
     st = ctx.stats()
     rows = ctx.query(X)

@@ -216,9 +216,14 @@ def map2d(seed):
                 boxes=M.cluster_boxes(), root_c=root_c, root_half=np.float32(root_half))
 
 
-def map3d(seed):
+def map3d(seed, variant=None, rtimes=None):
+    """variant / rtimes: a variant build of the reference with a params.h override (oracle/params_variants/), e.g.
+    "rtimes25" with rtimes=2.5: the larger training balls of BASELINE configs[4]."""
     rng = np.random.default_rng(seed)
-    P = H.P3
+    P = dict(H.P3)
+    if variant:
+        refpy.use_variant(variant)
+        P["rtimes"] = rtimes
     s = H.sphere_samples(0.12, 0.0125, (0.0517, 0.0231, 0.0113), rng)
     M = refpy.RefMap3()
     M.insert_samples(s)
@@ -235,18 +240,23 @@ def map3d(seed):
     rows = M.test(X, init.copy())
     ncand = np.array([M.candidates(q, P["search"])[0].shape[0] for q in X], np.int32)
     root_c, root_half = M.root()
-    return dict(samples_in=s, centres=centres, offsets=offs, samples=samples, X=X, init=init, rows=rows, ncand=ncand,
-                boxes=M.cluster_boxes(), root_c=root_c, root_half=np.float32(root_half))
+    out = dict(samples_in=s, centres=centres, offsets=offs, samples=samples, X=X, init=init, rows=rows, ncand=ncand,
+               boxes=M.cluster_boxes(), root_c=root_c, root_half=np.float32(root_half))
+    if variant:
+        refpy.use_variant(None)
+    return out
 
 
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:   # regenerate selected fixtures: python make_golden.py seq3d map2d seq2d_demo
         for name in only:
-            fn = {"seq3d": seq3d, "map2d": lambda: map2d(15), "seq2d_demo": seq2d_demo, "room40": room40, "seq2d": seq2d}[name]
+            fn = {"seq3d": seq3d, "map2d": lambda: map2d(15), "seq2d_demo": seq2d_demo, "room40": room40, "seq2d": seq2d,
+                  "map3d_rt25": lambda: map3d(16, "rtimes25", 2.5)}[name]
             np.savez_compressed(os.path.join(HERE, name + ".npz"), **fn())
             print(name, os.path.getsize(os.path.join(HERE, name + ".npz")))
         sys.exit(0)
+    np.savez_compressed(os.path.join(HERE, "map3d_rt25.npz"), **map3d(16, "rtimes25", 2.5))
     np.savez_compressed(os.path.join(HERE, "seq3d.npz"), **seq3d())
     np.savez_compressed(os.path.join(HERE, "map2d.npz"), **map2d(15))
     np.savez_compressed(os.path.join(HERE, "leaf3d.npz"), **leaf(3, 24, 11))

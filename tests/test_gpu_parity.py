@@ -107,7 +107,7 @@ def _fixture_map(cabi):
 
 
 @pytest.mark.parametrize("version", [3, 1])
-def test_query_matches_reference_fixture(cabi, oracle, oracle64, version):
+def test_query_matches_reference_fixture(cabi, oracle, oracle64r, version):
     """K3 + K4 against rows produced by the unmodified reference (tests/golden/map3d.npz): candidate
     counts bit-exact (incl. lattice-touching boxes), picks identical where the fixture has exact ties
     and > 16 candidates (std::sort replay), values within the stated tolerances."""
@@ -117,9 +117,9 @@ def test_query_matches_reference_fixture(cabi, oracle, oracle64, version):
     assert np.array_equal(chosen[:, 0], g["ncand"])
     offs = g["offsets"]
     gps = [oracle.gp_train(3, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
-    gps64 = [oracle64.gp_train(3, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
+    gps64 = [oracle64r.gp_train(3, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
     m = oracle.make_map(3, g["centres"], P["half"], gps, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
-    m64 = oracle64.make_map(3, g["centres"], P["half"], gps64, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
+    m64 = oracle64r.make_map(3, g["centres"], P["half"], gps64, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
     want, ochosen, otie = m.test(g["X"], g["init"].copy(), want_choice=True)
     want64 = m64.test(g["X"], g["init"].astype(np.float64))
     assert np.array_equal(want, g["rows"])                      # the oracle itself reproduces the fixture
@@ -133,12 +133,40 @@ def test_query_matches_reference_fixture(cabi, oracle, oracle64, version):
     assert np.array_equal(tie, otie)
     assert (tie > 0).sum() > 50
     ev = g["ncand"] > 0
-    H.check_rows(got[ev], g["rows"][ev], want64[ev], 3, label=f"v{version}")
+    evi = np.flatnonzero(ev)
+    H.check_rows(got[ev], g["rows"][ev], want64[ev], 3, label=f"v{version}",
+                 explain=lambda i: H.selection_ambiguity(gps64, ochosen[evi[i]], g["X"][evi[i]], P["var_thre"], 3))
     # read-modify-write: rows without candidates keep the caller's contents, var_f preset
     keep = [0, 1, 2, 3, 5, 6, 7]
     assert np.array_equal(got[~ev][:, keep], g["init"][~ev][:, keep])
     assert np.all(got[~ev][:, 4] == np.float32(1.0 + np.float32(5e-3)))
     ctx.close()
+
+
+def test_larger_training_balls_through_host_class(cabi, oracle, oracle64r):
+    """BASELINE configs[4] knob end to end on the GPU: the drop-in GPisMap3 with GPisMap3Tuning.rtimes = 2.5 against
+    rows of the reference rebuilt with GPISMAP3_RTIMES 2.5 (tests/golden/map3d_rt25.npz)."""
+    from gpismap_b200 import hostapi
+    g = dict(np.load(os.path.join(G, "map3d_rt25.npz")))
+    P = H.P3
+    m = hostapi.GPisMap3(rtimes=2.5)
+    assert m.insert_samples(g["samples_in"]) == len(g["samples_in"])
+    m.train_active()
+    assert np.array_equal(m.leaves()[0], g["centres"])
+    got = m.test(g["X"], g["init"].copy())
+    offs = g["offsets"]
+    gps = [oracle.gp_train(3, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
+    gps64 = [oracle64r.gp_train(3, g["samples"][offs[i]:offs[i + 1]], P["scale"], P["noise"]) for i in range(len(offs) - 1)]
+    mo = oracle.make_map(3, g["centres"], P["half"], gps, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
+    m64 = oracle64r.make_map(3, g["centres"], P["half"], gps64, P["search"], P["var_thre"], P["noise"], boxes=g["boxes"])
+    want, ochosen, _ = mo.test(g["X"], g["init"].copy(), want_choice=True)
+    assert np.array_equal(want, g["rows"])
+    want64 = m64.test(g["X"], g["init"].astype(np.float64))
+    ev = g["ncand"] > 0
+    evi = np.flatnonzero(ev)
+    H.check_rows(got[ev], g["rows"][ev], want64[ev], 3, label="rtimes 2.5",
+                 explain=lambda i: H.selection_ambiguity(gps64, ochosen[evi[i]], g["X"][evi[i]], P["var_thre"], 3))
+    m.close()
 
 
 def test_query_invariances(cabi):

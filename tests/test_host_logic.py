@@ -98,3 +98,20 @@ def test_3d_bundled_sequence_bit_exact(mocklib):
         assert len(S) == g["nsamples"][k] and m.leaves()[0].shape[0] == g["nleaves"][k], k
         if k + 1 == 5:
             assert np.array_equal(S, g["samples5"])
+
+
+def test_3d_larger_training_balls_match_reference_variant(mocklib):
+    """BASELINE configs[4] knob: GPisMap3Tuning.rtimes = 2.5 (the reference needs a rebuild with GPISMAP3_RTIMES 2.5,
+    oracle/params_variants/rtimes25). Fixture from that variant build: same leaves, same training sets (sizes), same rows."""
+    from gpismap_b200 import hostapi
+    g = dict(np.load(os.path.join(G, "map3d_rt25.npz")))
+    m = hostapi.GPisMap3(libpath=mocklib, rtimes=2.5)
+    assert m.insert_samples(g["samples_in"]) == len(g["samples_in"])
+    m.train_active()
+    c, n = m.leaves()
+    assert np.array_equal(c, g["centres"])
+    assert np.array_equal(m.test(g["X"], g["init"].copy()), g["rows"])
+    d = hostapi.GPisMap3(libpath=mocklib)            # default radius: different training sets, different rows
+    d.insert_samples(g["samples_in"])
+    d.train_active()
+    assert not np.array_equal(d.test(g["X"], g["init"].copy()), g["rows"])
