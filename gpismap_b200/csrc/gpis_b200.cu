@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "leaf_train.cuh"
+#include "gather.cuh"
 #include "obs_gp.cuh"
 #include "query.cuh"
 #include "query_group.cuh"
@@ -130,6 +131,9 @@ struct HostLeaf {
     float centre[3];
     float lo[3], hi[3];   // effective box (default: centre -/+ cluster_half)
     bool box_set;
+    uint64_t smp;      // device sample block of this leaf (gpis_samples_set), 0 = none
+    uint64_t smp_bytes;
+    int smp_n;
 };
 
 struct ArenaChunk { unsigned char* base; uint64_t size; };
@@ -159,6 +163,10 @@ struct gpis_ctx {
     void* d_scratch2 = nullptr; uint64_t scratch2_bytes = 0;
     void* d_jobs = nullptr; uint64_t jobs_bytes = 0;             // training jobs + status
     int num_sms = 148;
+    // device sample store (f-2)
+    SampleStore store{nullptr, nullptr};
+    std::vector<uint64_t> slot_key;                              // slot -> key of the leaf that owns it
+    void* d_gather = nullptr; uint64_t gather_bytes = 0;         // flags, dirty list, counts, offsets
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
@@ -271,6 +279,21 @@ static int table_alloc(gpis_ctx* ctx, uint32_t cap, int slot_cap) {
     CK(cudaMalloc(&N.meta, sizeof(int4) * slot_cap));
     CK(cudaMemsetAsync(N.cell, 0, sizeof(int4) * slot_cap, ctx->stream));
     CK(cudaMemsetAsync(N.rec, 0, sizeof(uint64_t) * slot_cap, ctx->stream));
+    if (slot_cap != ctx->slot_cap || !ctx->store.ptr) {   // the sample store is indexed by slot too
+        SampleStore S{nullptr, nullptr};
+        CK(cudaMalloc(&S.ptr, sizeof(uint64_t) * slot_cap));
+        CK(cudaMalloc(&S.cnt, sizeof(int32_t) * slot_cap));
+        CK(cudaMemsetAsync(S.ptr, 0, sizeof(uint64_t) * slot_cap, ctx->stream));
+        CK(cudaMemsetAsync(S.cnt, 0, sizeof(int32_t) * slot_cap, ctx->stream));
+        if (ctx->store.ptr) {
+            CK(cudaMemcpyAsync(S.ptr, ctx->store.ptr, sizeof(uint64_t) * ctx->slot_cap, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(S.cnt, ctx->store.cnt, sizeof(int32_t) * ctx->slot_cap, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt);
+        }
+        ctx->store = S;
+        ctx->slot_key.resize(slot_cap, 0);
+    }
     if (ctx->T.keys) {
         const int old = ctx->slot_cap;
         CK(cudaMemcpyAsync(N.centre, ctx->T.centre, sizeof(float4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -403,7 +426,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
     cudaFree(const_cast<int4*>(ctx->prog.recs)); cudaFree(const_cast<int32_t*>(ctx->prog.off));
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
-    cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_acc); cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt); cudaFree(ctx->d_gather);
     cudaFree(ctx->d_repl); cudaFree(ctx->d_repl_idx); cudaFree(ctx->d_repl_jobs);
     if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -428,6 +451,8 @@ int gpis_reset(gpis_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->T.keys, 0, sizeof(uint64_t) * ctx->table_cap, ctx->stream));
     CK(cudaMemsetAsync(ctx->T.cell, 0, sizeof(int4) * ctx->slot_cap, ctx->stream));
     CK(cudaMemsetAsync(ctx->T.rec, 0, sizeof(uint64_t) * ctx->slot_cap, ctx->stream));
+    CK(cudaMemsetAsync(ctx->store.ptr, 0, sizeof(uint64_t) * ctx->slot_cap, ctx->stream));
+    CK(cudaMemsetAsync(ctx->store.cnt, 0, sizeof(int32_t) * ctx->slot_cap, ctx->stream));
     ctx->obs_trained = false;
     ctx->obs_repartition = true;   // ObsGP2D::reset (ObsGP.cpp:198-203) runs when the map deletes gpo
     ctx->obs_ni = ctx->obs_nj = -1;
@@ -471,6 +496,18 @@ static int apply_updates(gpis_ctx* ctx, const std::vector<SlotUpdate>& ups) {
     return 0;
 }
 
+static int store_apply(gpis_ctx* ctx, const std::vector<StoreUpdate>& ups) {
+    if (ups.empty()) return 0;
+    int rc = ensure(ctx, &ctx->d_scratch2, &ctx->scratch2_bytes, ups.size() * sizeof(StoreUpdate));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_scratch2, ups.data(), ups.size() * sizeof(StoreUpdate), cudaMemcpyHostToDevice, ctx->stream));
+    k_store_apply<<<((int)ups.size() + 127) / 128, 128, 0, ctx->stream>>>(ctx->store, (const StoreUpdate*)ctx->d_scratch2, (int)ups.size());
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // centre / default box of a leaf; keeps an explicitly set box (gpis_leaves_set_boxes)
 static void set_geometry(gpis_ctx* ctx, HostLeaf& hl, const int32_t* cell, const float* centre) {
     const int dim = ctx->cfg.dim;
@@ -490,9 +527,13 @@ static SlotUpdate make_update(uint64_t key, const HostLeaf& hl) {
     return u;
 }
 
-static int take_slot(gpis_ctx* ctx) {
-    if (!ctx->free_slots.empty()) { int s = ctx->free_slots.back(); ctx->free_slots.pop_back(); return s; }
-    return ctx->slot_count++;
+static int take_slot(gpis_ctx* ctx, uint64_t key) {
+    int s;
+    if (!ctx->free_slots.empty()) { s = ctx->free_slots.back(); ctx->free_slots.pop_back(); }
+    else s = ctx->slot_count++;
+    if ((size_t)s >= ctx->slot_key.size()) ctx->slot_key.resize(s + 1, 0);
+    ctx->slot_key[s] = key;
+    return s;
 }
 
 int gpis_leaves_mark(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres) {
@@ -506,7 +547,7 @@ int gpis_leaves_mark(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const fl
         const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
         if (ctx->leaves.count(key)) continue;
         HostLeaf hl{};
-        hl.slot = take_slot(ctx);
+        hl.slot = take_slot(ctx, key);
         set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
         ctx->leaves[key] = hl;
         ups.push_back(make_update(key, hl));
@@ -538,6 +579,7 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
     CK(cudaSetDevice(ctx->cfg.device));
     const int dim = ctx->cfg.dim;
     std::vector<SlotUpdate> ups;
+    std::vector<StoreUpdate> store_clear;
     for (int i = 0; i < n_leaves; ++i) {
         const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
         auto it = ctx->leaves.find(key);
@@ -546,6 +588,7 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
         u.key = key; u.slot = it->second.slot; u.live = 0;
         ups.push_back(u);
         if (it->second.rec) arena_free(ctx, it->second.rec, it->second.rec_bytes);
+        if (it->second.smp) { arena_free(ctx, it->second.smp, it->second.smp_bytes); store_clear.push_back(StoreUpdate{it->second.slot, 0, 0ull}); }
         ctx->free_slots.push_back(it->second.slot);
         ctx->leaves.erase(it);
         ctx->tombs++;
@@ -553,6 +596,8 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
         ctx->repl_erased.push_back(key);
     }
     int rc = apply_updates(ctx, ups);
+    if (rc) return rc;
+    rc = store_apply(ctx, store_clear);
     if (rc) return rc;
     if (ctx->tombs * 4 > (int)ctx->table_cap) return table_alloc(ctx, ctx->table_cap, ctx->slot_cap);
     return 0;
@@ -645,7 +690,7 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
         auto it = ctx->leaves.find(key);
         if (it == ctx->leaves.end()) {
             HostLeaf hl{};
-            hl.slot = take_slot(ctx);
+            hl.slot = take_slot(ctx, key);
             it = ctx->leaves.emplace(key, hl).first;
         }
         HostLeaf& hl = it->second;
@@ -704,6 +749,180 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
     ctx->st.last_train_ms = ms;
     ctx->st.last_train_skipped = skipped;
     if (skipped) ctx->err = "gpis_leaves_update: " + std::to_string(skipped) + " leaf/leaves exceed GPIS_MAX_SAMPLES / GPIS_MAX_N and were not retrained (see status[])";
+    return GPIS_OK;
+}
+
+// ------------------------------------------------------------------ f-2: device sample store + device-side gather
+int gpis_samples_set(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres, const int32_t* offsets,
+                     const float* samples) {
+    if (!ctx || n_leaves < 0) return GPIS_ERR_ARG;
+    if (n_leaves == 0) return GPIS_OK;
+    if (!cells || !centres || !offsets || (offsets[n_leaves] > 0 && !samples)) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
+    for (int i = 0; i < n_leaves; ++i)
+        if (offsets[i] < 0 || offsets[i + 1] < offsets[i]) { ctx->err = "offsets must be non-negative and non-decreasing"; return GPIS_ERR_ARG; }
+    int rc = table_reserve(ctx, n_leaves);
+    if (rc) return rc;
+    const uint64_t total = (uint64_t)offsets[n_leaves] * w9 * sizeof(float);
+    rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, std::max<uint64_t>(total, 256));
+    if (rc) return rc;
+    if (total) CK(cudaMemcpyAsync(ctx->d_scratch, samples, total, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<SlotUpdate> ups;
+    std::vector<StoreUpdate> sup;
+    std::vector<WordCopy> jobs;
+    for (int i = 0; i < n_leaves; ++i) {
+        const uint64_t key = key_of(ctx, cells + (size_t)i * dim);
+        auto it = ctx->leaves.find(key);
+        if (it == ctx->leaves.end()) {   // not registered yet: register it like gpis_leaves_mark
+            HostLeaf hl{};
+            hl.slot = take_slot(ctx, key);
+            set_geometry(ctx, hl, cells + (size_t)i * dim, centres + (size_t)i * dim);
+            it = ctx->leaves.emplace(key, hl).first;
+            ups.push_back(make_update(key, it->second));
+            ctx->repl_touched.insert(key);
+        }
+        HostLeaf& hl = it->second;
+        const int N = offsets[i + 1] - offsets[i];
+        if (hl.smp) arena_free(ctx, hl.smp, hl.smp_bytes);
+        hl.smp = 0; hl.smp_bytes = 0; hl.smp_n = N;
+        if (N > 0) {
+            hl.smp_bytes = (uint64_t)N * w9 * sizeof(float);
+            rc = arena_alloc(ctx, hl.smp_bytes, &hl.smp);
+            if (rc) { hl.smp = 0; hl.smp_bytes = 0; hl.smp_n = 0; return rc; }
+            jobs.push_back(WordCopy{(const uint32_t*)ctx->d_scratch + (size_t)offsets[i] * w9, (uint32_t*)hl.smp, (uint64_t)N * w9});
+        }
+        sup.push_back(StoreUpdate{hl.slot, N, hl.smp});
+    }
+    if (!jobs.empty()) {
+        rc = ensure(ctx, &ctx->d_jobs, &ctx->jobs_bytes, jobs.size() * sizeof(WordCopy));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->d_jobs, jobs.data(), jobs.size() * sizeof(WordCopy), cudaMemcpyHostToDevice, ctx->stream));
+        k_copy_words<<<dim3((unsigned)jobs.size(), 1), 256, 0, ctx->stream>>>((const WordCopy*)ctx->d_jobs);
+        ctx->st.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    rc = store_apply(ctx, sup);     // synchronises: the host buffers above may go
+    if (rc) return rc;
+    return apply_updates(ctx, ups);
+}
+
+int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_cells, float radius, int32_t* n_trained) {
+    if (!ctx || n_active < 0 || !(radius > 0.f)) return GPIS_ERR_ARG;
+    if (n_trained) *n_trained = 0;
+    ctx->st.last_train_leaves = 0; ctx->st.last_train_ms = 0.f; ctx->st.last_train_skipped = 0;
+    if (n_active == 0) return GPIS_OK;
+    if (!active_cells) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
+    {   // the warp-local neighbour list holds GATHER_MAXNBR leaves
+        const double per_axis = 2.0 * std::ceil((double)radius * ctx->qp.inv_pitch) + 1.0;
+        if (std::pow(per_axis, dim) > GATHER_MAXNBR) { ctx->err = "training radius too large for the device-side gather"; return GPIS_ERR_CAPACITY; }
+    }
+    const int nslots = ctx->slot_count;
+    // scratch: [active int4 x n][flag x nslots][list x nslots][count 16][N x nslots][ng x nslots][off x nslots]
+    const uint64_t b_act = align_up(sizeof(int4) * (uint64_t)n_active, 256), b_sl = align_up(sizeof(int32_t) * (uint64_t)std::max(nslots, 1), 256);
+    int rc = ensure(ctx, &ctx->d_gather, &ctx->gather_bytes, b_act + 5 * b_sl + 256);
+    if (rc) return rc;
+    unsigned char* base = (unsigned char*)ctx->d_gather;
+    int4* d_act = (int4*)base;
+    int32_t* d_flag = (int32_t*)(base + b_act);
+    int32_t* d_list = (int32_t*)(base + b_act + b_sl);
+    int32_t* d_cnt = (int32_t*)(base + b_act + 2 * b_sl);
+    int32_t* d_N = (int32_t*)(base + b_act + 2 * b_sl + 256);
+    int32_t* d_ng = (int32_t*)(base + b_act + 3 * b_sl + 256);
+    int32_t* d_off = (int32_t*)(base + b_act + 4 * b_sl + 256);
+    std::vector<int4> act(n_active);
+    for (int i = 0; i < n_active; ++i) act[i] = make_int4(active_cells[(size_t)i * dim], active_cells[(size_t)i * dim + 1], dim == 3 ? active_cells[(size_t)i * dim + 2] : 0, 0);
+    CK(cudaMemcpyAsync(d_act, act.data(), sizeof(int4) * (uint64_t)n_active, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_flag, 0, b_sl, ctx->stream));
+    CK(cudaMemsetAsync(d_cnt, 0, 256, ctx->stream));
+    k_dirty_mark<<<(n_active + 127) / 128, 128, 0, ctx->stream>>>(d_act, n_active, ctx->T, ctx->qp, radius, d_flag, d_list, d_cnt);
+    ctx->st.kernel_launches++;
+    int32_t ndirty = 0;
+    CK(cudaMemcpyAsync(&ndirty, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ndirty <= 0) return GPIS_OK;
+    k_ball<0><<<(ndirty + 3) / 4, 128, 0, ctx->stream>>>(d_list, ndirty, ctx->T, ctx->qp, ctx->store, radius, d_N, d_ng, nullptr, nullptr);
+    ctx->st.kernel_launches++;
+    std::vector<int32_t> list(ndirty), hN(ndirty), hng(ndirty), off(ndirty, 0);
+    CK(cudaMemcpyAsync(list.data(), d_list, sizeof(int32_t) * ndirty, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hN.data(), d_N, sizeof(int32_t) * ndirty, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hng.data(), d_ng, sizeof(int32_t) * ndirty, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // plan: sizes, capacity, record reservation (rolled back on failure); nothing is installed before training succeeded
+    struct Plan { uint64_t key; int N, ng, n, nb; uint64_t rec, rb; };
+    std::vector<Plan> plan;
+    std::vector<int> plan_of(ndirty, -1);
+    int skipped = 0;
+    int64_t nrows = 0;
+    for (int d = 0; d < ndirty; ++d) {
+        off[d] = (int32_t)nrows;
+        const int N = hN[d];
+        if (N <= 0) continue;                                   // GPisMap3.cpp:710: empty ball, the leaf keeps its GP
+        const int n = N + dim * hng[d], nb = (n + 31) / 32;
+        if (N > GPIS_MAX_SAMPLES || n > GPIS_MAX_N) { ++skipped; continue; }
+        Plan pl{ctx->slot_key[list[d]], N, hng[d], n, nb, 0, rec_bytes(N, nb)};
+        rc = arena_alloc(ctx, pl.rb, &pl.rec);
+        if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
+        plan_of[d] = (int)plan.size();
+        plan.push_back(pl);
+        nrows += N;
+    }
+    if (plan.empty()) { ctx->st.last_train_skipped = skipped; return GPIS_OK; }
+    rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, (uint64_t)nrows * w9 * sizeof(float));
+    if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
+    // gather only the leaves that train: compact the dirty list to those
+    std::vector<int32_t> tlist, toff;
+    for (int d = 0; d < ndirty; ++d) if (plan_of[d] >= 0) { tlist.push_back(list[d]); toff.push_back(off[d]); }
+    CK(cudaMemcpyAsync(d_list, tlist.data(), sizeof(int32_t) * tlist.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, toff.data(), sizeof(int32_t) * toff.size(), cudaMemcpyHostToDevice, ctx->stream));
+    k_ball<1><<<((int)tlist.size() + 3) / 4, 128, 0, ctx->stream>>>(d_list, (int)tlist.size(), ctx->T, ctx->qp, ctx->store, radius, nullptr, nullptr,
+                                                                    d_off, (float*)ctx->d_scratch);
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    std::vector<TrainJob> jobs(plan.size());
+    double flops = 0, bytes = 0;
+    int64_t sumN = 0, sumn = 0;
+    int maxN = 1, maxnb = 1;
+    for (size_t i = 0; i < plan.size(); ++i) {
+        const Plan& pl = plan[i];
+        const HostLeaf& hl = ctx->leaves[pl.key];
+        TrainJob& j = jobs[i];
+        j = TrainJob{};
+        j.rec = pl.rec; j.sample_off = toff[i]; j.N = pl.N; j.ng = pl.ng; j.n = pl.n; j.nb = pl.nb; j.slot = hl.slot;
+        for (int c = 0; c < 3; ++c) { j.cell[c] = hl.cell[c]; j.centre[c] = hl.centre[c]; j.lo[c] = hl.lo[c]; j.hi[c] = hl.hi[c]; }
+        flops += (double)pl.n * pl.n * pl.n / 3.0 + 2.0 * pl.n * pl.n + 30.0 * pl.N * pl.N;
+        bytes += 52.0 * pl.N + 4.0 * pl.n + 2.0 * pl.n * (pl.n + 1.0);
+        sumN += pl.N; sumn += pl.n;
+        maxN = std::max(maxN, pl.N); maxnb = std::max(maxnb, pl.nb);
+    }
+    float ms = 0.f;
+    std::vector<int32_t> st(jobs.size(), 0);
+    rc = train_jobs(ctx, jobs, (const float*)ctx->d_scratch, maxN, maxnb, st.data(), &ms);
+    if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
+    std::vector<SlotUpdate> ups;
+    std::vector<std::pair<uint64_t, uint64_t>> to_free;
+    for (const Plan& pl : plan) {
+        HostLeaf& hl = ctx->leaves[pl.key];
+        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
+        hl.rec = pl.rec; hl.rec_bytes = pl.rb; hl.N = pl.N; hl.ng = pl.ng; hl.n = pl.n; hl.nb = pl.nb;
+        ups.push_back(make_update(pl.key, hl));
+        ctx->repl_touched.insert(pl.key);
+        ctx->repl_trained.insert(pl.key);
+    }
+    ctx->max_nb = std::max(ctx->max_nb, maxnb);
+    ctx->max_N = std::max(ctx->max_N, maxN);
+    rc = apply_updates(ctx, ups);
+    if (rc) return rc;
+    for (auto& f : to_free) arena_free(ctx, f.first, f.second);
+    ctx->st.last_train_leaves = (int64_t)jobs.size();
+    ctx->st.last_train_sum_N = sumN; ctx->st.last_train_sum_n = sumn;
+    ctx->st.last_train_flops = flops; ctx->st.last_train_bytes = bytes;
+    ctx->st.last_train_ms = ms;
+    ctx->st.last_train_skipped = skipped;
+    if (n_trained) *n_trained = (int32_t)jobs.size();
+    if (skipped) ctx->err = "gpis_leaves_train_dirty: " + std::to_string(skipped) + " leaf/leaves exceed GPIS_MAX_SAMPLES / GPIS_MAX_N and were not retrained";
     return GPIS_OK;
 }
 
@@ -1102,6 +1321,7 @@ static int erase_one(gpis_ctx* ctx, uint64_t key, std::vector<SlotUpdate>& ups) 
     u.key = key; u.slot = it->second.slot; u.live = 0;
     ups.push_back(u);
     if (it->second.rec) arena_free(ctx, it->second.rec, it->second.rec_bytes);
+    if (it->second.smp) arena_free(ctx, it->second.smp, it->second.smp_bytes);   // replicas hold no samples; kept for symmetry
     ctx->free_slots.push_back(it->second.slot);
     ctx->leaves.erase(it);
     ctx->tombs++;
@@ -1215,7 +1435,7 @@ static int receive_install(gpis_ctx* ctx, const ReplHeader& hd, const std::vecto
         auto it = ctx->leaves.find(e.key);
         if (it == ctx->leaves.end()) {
             HostLeaf hl{};
-            hl.slot = take_slot(ctx);
+            hl.slot = take_slot(ctx, e.key);
             it = ctx->leaves.emplace(e.key, hl).first;
         }
         HostLeaf& hl = it->second;

@@ -223,6 +223,7 @@ void GPisMap::Impl::reeval_apply(const ReEval& e, const float* rinv0, const floa
     if ((double)norm_grad_new < 1e-3) {
         old.pose_sig = (float)(2.0 * (double)old.pose_sig);
         old.grad_sig = (float)(2.0 * (double)old.grad_sig);
+        tree->touch(e.sample);
         return;
     }
     float r_var = (float)((double)r0_sqr_sum / 3.0 - (double)(r0_mean * r0_mean) * 4.0 / 3.0);

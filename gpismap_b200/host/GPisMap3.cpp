@@ -353,6 +353,7 @@ void GPisMap3::Impl::reeval_commit(const ReEval& e, const ReOut& o) {
         Sample<3>& old = tree->sample(e.sample);
         old.pose_sig = (float)(2.0 * (double)old.pose_sig);
         old.grad_sig = (float)(2.0 * (double)old.grad_sig);
+        tree->touch(e.sample);
         return;
     }
     const float noise = o.noise, grad_noise = o.grad_noise;

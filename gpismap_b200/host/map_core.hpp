@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -57,6 +58,11 @@ public:
     std::map<uint64_t, std::array<float, 6>> device_boxes;     // effective boxes sent for them (only non-default ones)
     int last_trained = 0;
     float last_train_ms = 0.f;
+    // device-side dirty set + training-set gather: the samples live on the device per leaf; the host
+    // re-sends only the leaves whose samples changed (mutation log of the tree). GPIS_HOST_GATHER=1 keeps the first
+    // path (host QueryRange per dirty leaf, gpis_leaves_update); results are identical.
+    bool device_gather = std::getenv("GPIS_HOST_GATHER") == nullptr || std::atoi(std::getenv("GPIS_HOST_GATHER")) == 0;
+    std::vector<std::pair<int32_t, uint32_t>> sample_log;
 
     bool ensure_ctx(const gpis_config& cfg) {
         if (ctx) return true;
@@ -71,13 +77,14 @@ public:
         }
         return true;
     }
-    void ensure_tree() { if (!tree) tree = new Tree(tparam); }   // addNewMeas, GPisMap3.cpp:573-575
+    void ensure_tree() { if (!tree) { tree = new Tree(tparam); tree->mutation_log = &sample_log; } }   // addNewMeas, GPisMap3.cpp:573-575
 
     void reset() {   // GPisMap3::reset, GPisMap3.cpp:99-115
         delete tree; tree = nullptr;
         active.clear();
         device_cells.clear();
         device_boxes.clear();
+        sample_log.clear();
         if (ctx) gpis_reset(ctx);
     }
 
@@ -129,9 +136,77 @@ public:
 
     // updateGPs: dirty set = active ∪ leaves whose box touches AABB(c, Rtimes*l), then one training
     // ball per dirty leaf, in QueryRange order, shipped as one CSR batch.
+    // f-2 path: table first (new leaves, erases, effective boxes, root box), then the changed sample lists, then the
+    // active cells; dirty-set expansion, ball gather and training happen on the device.
+    // Returns 1 = done, 0 = not applicable (fall back to the host gather), -1 = error.
+    int train_active_device() {
+        if (!sync_table()) return -1;
+        constexpr int W = 2 * D + 3;
+        double tp0 = now_s();
+        {
+            std::sort(sample_log.begin(), sample_log.end());
+            sample_log.erase(std::unique(sample_log.begin(), sample_log.end()), sample_log.end());
+            std::vector<int32_t> cells, offsets(1, 0);
+            std::vector<float> centres, samples;
+            std::vector<int> ids;
+            for (auto& e : sample_log) {
+                if (!tree->cell_alive(e.first, e.second)) continue;      // collapsed: sync_table erased it
+                const auto& n = tree->cell(e.first);
+                int32_t cc[3];
+                cell_of(e.first, cc);
+                ids.clear();
+                tree->collect_samples(e.first, ids);
+                if (ids.empty() && !device_cells.count(pack(cc))) continue;
+                for (int a = 0; a < D; ++a) { cells.push_back(cc[a]); centres.push_back(n.c[a]); }
+                for (int s : ids) {
+                    const Sample<D>& sm = tree->sample(s);
+                    for (int a = 0; a < D; ++a) samples.push_back(sm.pos[a]);
+                    for (int a = 0; a < D; ++a) samples.push_back(sm.grad[a]);
+                    samples.push_back(sm.val); samples.push_back(sm.pose_sig); samples.push_back(sm.grad_sig);
+                }
+                offsets.push_back((int32_t)(samples.size() / W));
+            }
+            sample_log.clear();
+            const int nl = (int)offsets.size() - 1;
+            if (nl > 0 && gpis_samples_set(ctx, nl, cells.data(), centres.data(), offsets.data(), samples.data()) != GPIS_OK) {
+                std::fprintf(stderr, "gpismap_b200: gpis_samples_set failed: %s\n", gpis_last_error(ctx));
+                return -1;
+            }
+        }
+        g_prof_s[6] += now_s() - tp0; g_prof_n[6] += 1;
+        std::vector<int32_t> acells;
+        float radius = rtimes_ * tparam.cluster_half;
+        for (const LeafHandle& h : active) {
+            if (!tree->cell_alive(h.cell, h.gen) || tree->is_empty_leaf(h.cell)) continue;
+            int32_t cc[3];
+            cell_of(h.cell, cc);
+            for (int a = 0; a < D; ++a) acells.push_back(cc[a]);
+            radius = rtimes_ * tree->cell(h.cell).half;                 // GPisMap3.cpp:733: Rtimes * l
+        }
+        active.clear();                                                   // GPisMap3.cpp:789
+        if (acells.empty()) return 1;
+        ProfScope ps(7);
+        int32_t ntr = 0;
+        const int rc = gpis_leaves_train_dirty(ctx, (int)acells.size() / D, acells.data(), radius, &ntr);
+        if (rc != GPIS_OK) {
+            std::fprintf(stderr, "gpismap_b200: gpis_leaves_train_dirty failed (%d): %s\n", rc, gpis_last_error(ctx));
+            return -1;
+        }
+        gpis_stats st;
+        gpis_get_stats(ctx, &st);
+        last_trained = (int)st.last_train_leaves;
+        last_train_ms = st.last_train_ms;
+        return 1;
+    }
+
     bool train_active() {
         last_trained = 0; last_train_ms = 0.f;
         if (!tree || !ctx) { active.clear(); return false; }
+        if (device_gather) {
+            const int r = train_active_device();
+            if (r != 0) return r > 0;
+        }
+        sample_log.clear();
         std::set<int> update_set;
         std::vector<int> qs;
         double tp0 = now_s();

@@ -119,6 +119,25 @@ public:
             for (int a = 0; a < D; ++a) { lo[a] = std::max(lo[a], cells_[p].lo[a]); hi[a] = std::min(hi[a], cells_[p].hi[a]); }
     }
 
+    // Every placement or removal of a sample is reported as the (cluster-level cell, generation) it happened under,
+    // so that the owner can keep a per-leaf copy of the samples elsewhere (the device sample store).
+    std::vector<std::pair<int32_t, uint32_t>>* mutation_log = nullptr;
+
+    // a sample's fields were changed in place (reEvalPoints doubling the noises, GPisMap3.cpp:451-454): log its leaf
+    void touch(int s) {
+        if (!mutation_log) return;
+        const float* p = samples_[s].pos;
+        int id = root_;
+        while (id >= 0) {
+            if (is_cluster_level(id)) { mutation_log->push_back({id, cells_[id].gen}); return; }
+            if (cells_[id].child0 < 0) return;
+            int nx = -1;
+            for (int k = 0; k < NCH; ++k)
+                if (contains(cells_[cells_[id].child0 + k], p)) { nx = cells_[id].child0 + k; break; }
+            id = nx;
+        }
+    }
+
     size_t num_cells() const { return cells_.size(); }
     size_t num_samples() const { return samples_.size(); }
 
@@ -203,6 +222,12 @@ private:
         for (int k = 0; k < NCH; ++k) s += cells_[n.child0 + k].count;
         n.count = s;
     }
+    void log_mutation(int id) {
+        if (!mutation_log) return;
+        int c = id;
+        while (c >= 0 && (double)cells_[c].half < (double)P.cluster_half - 1e-3) c = cells_[c].parent;
+        if (c >= 0 && is_cluster_level(c)) mutation_log->push_back({c, cells_[c].gen});
+    }
     bool reg_ok(const Cell& n) const { return std::fabs((double)n.half - (double)P.cluster_half) < (double)P.reg_tol_insert; }
 
     // InsertToParent (octree.cpp:151-212): the root grows toward the point; the old root becomes
@@ -280,6 +305,7 @@ private:
         if (cells_[id].max_depth) {
             if (cells_[id].sample < 0) {
                 cells_[id].sample = s; cells_[id].count = 1;
+                log_mutation(id);
                 if (quads && P.reg_at_maxdepth && reg_ok(cells_[id])) quads->push_back(id);
                 return true;
             }
@@ -291,6 +317,7 @@ private:
             } else {
                 if (cells_[id].sample < 0) {
                     cells_[id].sample = s; cells_[id].count = 1;
+                    log_mutation(id);
                     if (quads && reg_ok(cells_[id])) quads->push_back(id);
                     return true;
                 }
@@ -305,6 +332,7 @@ private:
                             if (insert_rec(cells_[id].child0 + k, old, quads)) break;
                 }
                 cells_[id].sample = -1;   // dropped silently if no child took it (lattice-plane rejection)
+                log_mutation(id);
             }
         }
         const int ck = certain_child(cells_[id], p);
@@ -335,6 +363,7 @@ private:
         if (is_empty_leaf(id)) return false;
         if (cells_[id].sample >= 0 && (double)sqdist(samples_[cells_[id].sample].pos, p) < 1e-12) {   // EPS, octree.cpp:22
             cells_[id].sample = -1; cells_[id].count = 0;
+            log_mutation(id);
             return true;
         }
         if (cells_[id].child0 < 0) return false;

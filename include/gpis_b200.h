@@ -95,6 +95,25 @@ int gpis_device(const gpis_ctx* ctx);
 int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres,
                        const int32_t* offsets, const float* samples, int32_t* status);
 
+/* ---- device-side dirty set and training-set gather ---------------------------------------------
+ * Instead of walking its tree once per dirty leaf and shipping every training ball (gpis_leaves_update), the host keeps
+ * the samples on the device, one block per leaf, and only re-sends the leaves whose samples changed:
+ *   gpis_samples_set        replace the sample lists of n_leaves leaves. CSR like gpis_leaves_update, but `samples` holds
+ *                           each leaf's OWN samples, in the tree's DFS order (getAllChildrenNonEmptyNodes,
+ *                           octree.cpp:806-827). An empty range drops the leaf's list. Unknown leaves are registered
+ *                           (untrained). Leaves removed with gpis_leaves_erase lose their list.
+ *   gpis_leaves_train_dirty replaces updateGPs for the leaves in `active_cells` (GPisMap3.cpp:720-792,
+ *                           GPisMap.cpp:596-663): the device expands them to the dirty set (every registered leaf whose
+ *                           effective box touches AABB(centre, radius), inclusive float compare), gathers each dirty
+ *                           leaf's training ball (samples with |p - c|^2 < radius^2 in the reference's float arithmetic,
+ *                           in QueryRange's DFS order) from the sample store, trains (K1) and installs the records.
+ *                           radius = Rtimes * cluster_half (GPisMap3.cpp:707,733) or 4 * cluster_half (GPisMap.cpp).
+ *                           The leaf table (boxes, root box: gpis_leaves_mark / _set_boxes / _rebase) must be current.
+ * Results are identical to the host-gather path (tests/test_gpu_parity.py::test_device_gather_equals_host_gather). */
+int gpis_samples_set(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres, const int32_t* offsets,
+                     const float* samples);
+int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_cells, float radius, int32_t* n_trained);
+
 /* Register leaves that hold samples but have no GP yet (a sample inserted through root growth
  * does not activate its leaf, octree.cpp:297-301, 209-211); they still count as query
  * candidates (octree.cpp:861-893). */

@@ -22,6 +22,7 @@ struct MockLeaf {
     gpo_gp* gp = nullptr;
     int N = 0;
     int index = 0;
+    std::vector<float> own;   // the leaf's own samples (gpis_samples_set)
 };
 struct gpis_ctx {
     gpis_config cfg;
@@ -93,6 +94,72 @@ int gpis_leaves_update(gpis_ctx* c, int n, const int32_t* cells, const float* ce
         if (status) status[i] = gpo_gp_chol_fail(L.gp);
         c->st.last_train_leaves++;
     }
+    return GPIS_OK;
+}
+// f-2 on the CPU, written independently of the CUDA kernels: flat scan over all leaves instead of a hash lookup.
+static void box_of(const gpis_ctx* c, const MockLeaf& L, float* lo, float* hi) {
+    for (int a = 0; a < c->cfg.dim; ++a) {
+        lo[a] = L.box_set ? L.lo[a] : L.centre[a] - c->cfg.cluster_half;
+        hi[a] = L.box_set ? L.hi[a] : L.centre[a] + c->cfg.cluster_half;
+    }
+}
+static bool touches(const gpis_ctx* c, const MockLeaf& L, const float* centre, float radius) {
+    float lo[3], hi[3];
+    box_of(c, L, lo, hi);
+    for (int a = 0; a < c->cfg.dim; ++a) {
+        const float qlo = centre[a] - radius, qhi = centre[a] + radius;
+        if (qhi < lo[a] || qlo > hi[a]) return false;
+    }
+    return true;
+}
+int gpis_samples_set(gpis_ctx* c, int n, const int32_t* cells, const float* centres, const int32_t* offsets, const float* samples) {
+    const int dim = c->cfg.dim, w = 2 * dim + 3;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int32_t> key(cells + (size_t)i * dim, cells + (size_t)(i + 1) * dim);
+        if (!c->leaves.count(key)) {
+            MockLeaf& L = c->leaves[key];
+            L.index = c->next_index++;
+            for (int a = 0; a < dim; ++a) { L.cell[a] = key[a]; L.centre[a] = centres[(size_t)i * dim + a]; }
+        }
+        MockLeaf& L = c->leaves[key];
+        L.own.assign(samples + (size_t)offsets[i] * w, samples + (size_t)offsets[i + 1] * w);
+    }
+    return GPIS_OK;
+}
+int gpis_leaves_train_dirty(gpis_ctx* c, int n_active, const int32_t* active, float radius, int32_t* n_trained) {
+    const int dim = c->cfg.dim, w = 2 * dim + 3;
+    c->st.last_train_leaves = 0;
+    std::vector<MockLeaf*> dirty;
+    for (int i = 0; i < n_active; ++i) {
+        std::vector<int32_t> key(active + (size_t)i * dim, active + (size_t)(i + 1) * dim);
+        auto it = c->leaves.find(key);
+        if (it == c->leaves.end()) continue;
+        for (auto& kv : c->leaves)
+            if (&kv.second == &it->second || touches(c, kv.second, it->second.centre, radius))
+                if (std::find(dirty.begin(), dirty.end(), &kv.second) == dirty.end()) dirty.push_back(&kv.second);
+    }
+    const float r2 = radius * radius;
+    for (MockLeaf* D : dirty) {
+        std::vector<std::pair<uint64_t, const MockLeaf*>> nb;
+        for (auto& kv : c->leaves)
+            if (touches(c, kv.second, D->centre, radius)) nb.push_back({dfs_key(c, kv.second.cell), &kv.second});
+        std::sort(nb.begin(), nb.end(), [](const std::pair<uint64_t, const MockLeaf*>& a, const std::pair<uint64_t, const MockLeaf*>& b) { return a.first < b.first; });
+        std::vector<float> ball;
+        for (auto& e : nb)
+            for (size_t k = 0; k + w <= e.second->own.size(); k += w) {
+                const float* s = e.second->own.data() + k;
+                float sq = 0.f;
+                for (int a = 0; a < dim; ++a) { const float d = s[a] - D->centre[a]; sq = (a == 0) ? d * d : sq + d * d; }
+                if (sq < r2) ball.insert(ball.end(), s, s + w);
+            }
+        const int N = (int)(ball.size() / w);
+        if (N <= 0) continue;
+        gpo_gp_free(D->gp);
+        D->gp = gpo_gp_train(dim, ball.data(), N, c->cfg.map_scale, c->cfg.map_noise);
+        D->N = N;
+        c->st.last_train_leaves++;
+    }
+    if (n_trained) *n_trained = (int32_t)c->st.last_train_leaves;
     return GPIS_OK;
 }
 int gpis_leaves_mark(gpis_ctx* c, int n, const int32_t* cells, const float* centres) {

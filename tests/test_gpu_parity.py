@@ -169,6 +169,41 @@ def test_larger_training_balls_through_host_class(cabi, oracle, oracle64r):
     m.close()
 
 
+def test_device_gather_equals_host_gather(cabi):
+    """f-2: the device-side dirty set + training-set gather (sample store per leaf, flat lookup, DFS-ordered balls)
+    must train exactly what the host tree walk trains: two maps of the same frames, one per path, answer a query
+    grid bit-identically (identical training sets in identical row order give identical records), in 3-D and 2-D."""
+    from gpismap_b200 import hostapi, synth
+    X = synth.query_grid(80)
+    rows, trained = [], []
+    for host_gather in ("1", "0"):
+        os.environ["GPIS_HOST_GATHER"] = host_gather
+        m = hostapi.GPisMap3()
+        n = 0
+        for k in range(5):
+            dz, pose = synth.frame(k, 40)
+            m.update(dz, pose)
+            n += m.timing()[1][2]
+        rows.append(m.test(X))
+        trained.append(int(n))
+        m.close()
+    os.environ.pop("GPIS_HOST_GATHER")
+    assert trained[0] == trained[1] and trained[0] > 2000, trained
+    assert (rows[0][:, 4] < 1).sum() > 10000
+    assert np.array_equal(rows[0], rows[1])
+    g = dict(np.load(os.path.join(G, "seq2d_demo.npz")))
+    rows = []
+    for host_gather in ("1", "0"):
+        os.environ["GPIS_HOST_GATHER"] = host_gather
+        m = hostapi.GPisMap()
+        for i in range(12):
+            m.update(g["thetas"], g["ranges"][i], g["pose6"][i])
+        rows.append(m.test(g["X"]))
+        m.close()
+    os.environ.pop("GPIS_HOST_GATHER")
+    assert np.array_equal(rows[0], rows[1])
+
+
 def test_query_invariances(cabi):
     """Size-independent properties: results do not depend on batch composition (grouping by leaf,
     chunking, order): permuted and split batches are bit-identical to the single batch."""
