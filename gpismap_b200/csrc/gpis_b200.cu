@@ -9,6 +9,7 @@
 #include <nccl.h>   // types only: the library is resolved at run time (gpis_comm_init), there is no link dependency
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 
 #include "common.cuh"
 #include "leaf_train.cuh"
+#include "frame.cuh"
 #include "gather.cuh"
 #include "obs_gp.cuh"
 #include "query.cuh"
@@ -167,6 +169,7 @@ struct gpis_ctx {
     SampleStore store{nullptr, nullptr};
     std::vector<uint64_t> slot_key;                              // slot -> key of the leaf that owns it
     void* d_gather = nullptr; uint64_t gather_bytes = 0;         // flags, dirty list, counts, offsets
+    void* d_frame = nullptr; uint64_t frame_bytes = 0;           // per-frame sensor pipeline (gpis_frame_eval)
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
@@ -426,7 +429,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
     cudaFree(const_cast<int4*>(ctx->prog.recs)); cudaFree(const_cast<int32_t*>(ctx->prog.off));
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
-    cudaFree(ctx->d_acc); cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt); cudaFree(ctx->d_gather);
+    cudaFree(ctx->d_acc); cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt); cudaFree(ctx->d_gather); cudaFree(ctx->d_frame);
     cudaFree(ctx->d_repl); cudaFree(ctx->d_repl_idx); cudaFree(ctx->d_repl_jobs);
     if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -815,6 +818,9 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     if (!active_cells) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
+    static const bool prof = std::getenv("GPIS_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tq[8] = {0}; tq[0] = now();
     {   // the warp-local neighbour list holds GATHER_MAXNBR leaves
         const double per_axis = 2.0 * std::ceil((double)radius * ctx->qp.inv_pitch) + 1.0;
         if (std::pow(per_axis, dim) > GATHER_MAXNBR) { ctx->err = "training radius too large for the device-side gather"; return GPIS_ERR_CAPACITY; }
@@ -842,6 +848,7 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     int32_t ndirty = 0;
     CK(cudaMemcpyAsync(&ndirty, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    tq[1] = now();
     if (ndirty <= 0) return GPIS_OK;
     k_ball<0><<<(ndirty + 3) / 4, 128, 0, ctx->stream>>>(d_list, ndirty, ctx->T, ctx->qp, ctx->store, radius, d_N, d_ng, nullptr, nullptr);
     ctx->st.kernel_launches++;
@@ -850,6 +857,7 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     CK(cudaMemcpyAsync(hN.data(), d_N, sizeof(int32_t) * ndirty, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hng.data(), d_ng, sizeof(int32_t) * ndirty, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    tq[2] = now();
     // plan: sizes, capacity, record reservation (rolled back on failure); nothing is installed before training succeeded
     struct Plan { uint64_t key; int N, ng, n, nb; uint64_t rec, rb; };
     std::vector<Plan> plan;
@@ -899,8 +907,10 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     }
     float ms = 0.f;
     std::vector<int32_t> st(jobs.size(), 0);
+    tq[3] = now();
     rc = train_jobs(ctx, jobs, (const float*)ctx->d_scratch, maxN, maxnb, st.data(), &ms);
     if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
+    tq[4] = now();
     std::vector<SlotUpdate> ups;
     std::vector<std::pair<uint64_t, uint64_t>> to_free;
     for (const Plan& pl : plan) {
@@ -922,6 +932,8 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     ctx->st.last_train_ms = ms;
     ctx->st.last_train_skipped = skipped;
     if (n_trained) *n_trained = (int32_t)jobs.size();
+    if (prof) std::fprintf(stderr, "train_dirty: mark %.2f count %.2f plan+gather-launch %.2f train(wall) %.2f [kernel %.2f] install %.2f ms, %d dirty, %zu trained\n",
+                           tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], ms, now() - tq[4], ndirty, jobs.size());
     if (skipped) ctx->err = "gpis_leaves_train_dirty: " + std::to_string(skipped) + " leaf/leaves exceed GPIS_MAX_SAMPLES / GPIS_MAX_N and were not retrained";
     return GPIS_OK;
 }
@@ -1102,14 +1114,12 @@ static int obs_upload_partition(gpis_ctx* ctx) {
     return 0;
 }
 
-int gpis_obs_train_2d(gpis_ctx* ctx, const float* vu, const float* zinv, int ni, int nj) {
-    if (!ctx) return GPIS_ERR_ARG;
-    if (!vu || !zinv || ni <= 0 || nj <= 0) return GPIS_OK;   // ObsGP.cpp:333: silently untrained
-    CK(cudaSetDevice(ctx->cfg.device));
+// computePartition (ObsGP.cpp:204-265) from the host copy of the pixel grid; recomputed only when the grid size
+// changes or after a reset, like the reference (ObsGP.cpp:335-337).
+static int obs_partition_2d(gpis_ctx* ctx, const float* vu, int ni, int nj) {
     const int g = 5, ov = 3;                                   // params.h:109-110
     ctx->op.d = 2; ctx->op.ni = ni; ctx->op.margin = 0.005f;   // params.h:108
     if (ctx->obs_ni != ni || ctx->obs_nj != nj || ctx->obs_repartition) {
-        // computePartition, ObsGP.cpp:204-265
         const int ng0 = (ni - ov) / g + 1, ng1 = (nj - ov) / g + 1;
         if (ng0 < 1 || ng1 < 1) { ctx->err = "grid too small for the ObsGP partition"; return GPIS_ERR_ARG; }
         std::vector<int> i0(ng0), i1(ng0), j0(ng1), j1(ng1);
@@ -1131,11 +1141,19 @@ int gpis_obs_train_2d(gpis_ctx* ctx, const float* vu, const float* zinv, int ni,
         ctx->op.ng0 = ng0; ctx->op.ntiles = ng0 * ng1;
         ctx->op.nb0 = (int)ctx->obs_hb0.size(); ctx->op.nb1 = (int)ctx->obs_hb1.size();
         ctx->obs_ni = ni; ctx->obs_nj = nj; ctx->obs_repartition = false;
-        int rc = obs_upload_partition(ctx);
-        if (rc) return rc;
+        return obs_upload_partition(ctx);
     }
+    return 0;
+}
+
+int gpis_obs_train_2d(gpis_ctx* ctx, const float* vu, const float* zinv, int ni, int nj) {
+    if (!ctx) return GPIS_ERR_ARG;
+    if (!vu || !zinv || ni <= 0 || nj <= 0) return GPIS_OK;   // ObsGP.cpp:333: silently untrained
+    CK(cudaSetDevice(ctx->cfg.device));
+    int rc = obs_partition_2d(ctx, vu, ni, nj);
+    if (rc) return rc;
     const uint64_t bx = align_up(sizeof(float) * 2 * (uint64_t)ni * nj, 256), bf = align_up(sizeof(float) * (uint64_t)ni * nj, 256);
-    int rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, bx + bf);
+    rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, bx + bf);
     if (rc) return rc;
     float* d_vu = (float*)ctx->d_scratch;
     float* d_f = (float*)((unsigned char*)ctx->d_scratch + bx);
@@ -1240,6 +1258,88 @@ int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, floa
     if (rc) return rc;
     CK(cudaMemcpyAsync(val, d_val, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(var, d_var, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPIS_OK;
+}
+
+// ------------------------------------------------------------------ f-3 + f-1: one depth frame on the device
+int gpis_frame_eval(gpis_ctx* ctx, const float* depth, int N, const float* vu_grid, const gpis_frame_params* fp,
+                    int32_t* n_valid, float* range_obs_max, int32_t cap, float* xyz_global, int32_t* status,
+                    float* grad, float* noise, float* grad_noise) {
+    if (!ctx || !depth || !vu_grid || !fp || !n_valid || !range_obs_max || N < 1) return GPIS_ERR_ARG;
+    if (ctx->cfg.dim != 3 || fp->skip < 1) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    FrameParams P{};
+    P.width = fp->width; P.height = fp->height; P.skip = fp->skip;
+    P.n = fp->width / fp->skip; P.m = fp->height / fp->skip; P.N = N;
+    for (int i = 0; i < 3; ++i) P.t[i] = fp->pose[i];
+    for (int i = 0; i < 9; ++i) P.R[i] = fp->pose[3 + i];
+    P.delx = fp->delx; P.obs_var_thre = fp->obs_var_thre;
+    P.min_position_noise = fp->min_position_noise; P.min_grad_noise = fp->min_grad_noise;
+    P.max_range = fp->max_range; P.min_range = fp->min_range;
+    const int G = P.n * P.m;
+    if (G < 1) return GPIS_ERR_ARG;
+    *n_valid = 0; *range_obs_max = 0.f;
+    int rc = obs_partition_2d(ctx, vu_grid, P.m, P.n);          // ni = rows (fast), nj = columns (GPisMap3.cpp:247-249)
+    if (rc) return rc;
+    // device layout (floats unless noted), sized for K = G
+    const uint64_t a = 256;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { const uint64_t r = o; o += align_up(bytes, a); return r; };
+    const uint64_t o_depth = take(4ull * N), o_vu = take(8ull * G), o_zinv = take(4ull * G), o_flag = take(4ull * G), o_start = take(4ull * (G + 1)),
+                   o_cur = take(4ull * G), o_vuv = take(8ull * G), o_xl = take(12ull * G), o_xg = take(12ull * G), o_val1 = take(4ull * G),
+                   o_var1 = take(4ull * G), o_vup = take(48ull * G), o_valp = take(24ull * G), o_varp = take(24ull * G), o_st = take(4ull * G),
+                   o_grad = take(12ull * G), o_noise = take(4ull * G), o_gn = take(4ull * G), o_tile = take(24ull * G), o_order = take(24ull * G),
+                   o_tc = take(4ull * (ctx->op.ntiles + 4096)), o_ts = take(4ull * (ctx->op.ntiles + 4096)), o_tcur = take(4ull * (ctx->op.ntiles + 4096)),
+                   o_rmax = take(256);
+    rc = ensure(ctx, &ctx->d_frame, &ctx->frame_bytes, o);
+    if (rc) return rc;
+    unsigned char* B = (unsigned char*)ctx->d_frame;
+    float* d_depth = (float*)(B + o_depth); float* d_vu = (float*)(B + o_vu); float* d_zinv = (float*)(B + o_zinv);
+    int32_t* d_flag = (int32_t*)(B + o_flag); int32_t* d_start = (int32_t*)(B + o_start); int32_t* d_cur = (int32_t*)(B + o_cur);
+    float* d_vuv = (float*)(B + o_vuv); float* d_xl = (float*)(B + o_xl); float* d_xg = (float*)(B + o_xg);
+    float* d_val1 = (float*)(B + o_val1); float* d_var1 = (float*)(B + o_var1); float* d_vup = (float*)(B + o_vup);
+    float* d_valp = (float*)(B + o_valp); float* d_varp = (float*)(B + o_varp); int32_t* d_st = (int32_t*)(B + o_st);
+    float* d_grad = (float*)(B + o_grad); float* d_noise = (float*)(B + o_noise); float* d_gn = (float*)(B + o_gn);
+    int32_t* d_tile = (int32_t*)(B + o_tile); int32_t* d_order = (int32_t*)(B + o_order);
+    int32_t* d_tc = (int32_t*)(B + o_tc); int32_t* d_ts = (int32_t*)(B + o_ts); int32_t* d_tcur = (int32_t*)(B + o_tcur);
+    int32_t* d_rmax = (int32_t*)(B + o_rmax);
+    CK(cudaMemcpyAsync(d_depth, depth, 4ull * N, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_vu, vu_grid, 8ull * G, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_rmax, 0, 256, ctx->stream));
+    const int gb = (G + 255) / 256;
+    k_frame_valid<<<gb, 256, 0, ctx->stream>>>(d_depth, P, d_zinv, d_flag);
+    k_obs_scan<<<1, 1024, 0, ctx->stream>>>(d_flag, G, d_start, d_cur);
+    k_frame_project<<<gb, 256, 0, ctx->stream>>>(d_depth, d_vu, P, d_flag, d_start, d_vuv, d_xl, d_xg, d_rmax);
+    ctx->st.kernel_launches += 3;
+    int32_t hk[2] = {0, 0};
+    CK(cudaMemcpyAsync(&hk[0], d_start + G, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&hk[1], d_rmax, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int K = hk[0];
+    *n_valid = K;
+    std::memcpy(range_obs_max, &hk[1], 4);
+    if (K <= 1) return GPIS_OK;                                  // GPisMap3.cpp:212-215: nothing to regress
+    if (K > cap || !xyz_global || !status || !grad || !noise || !grad_noise) { ctx->err = "gpis_frame_eval: output capacity"; return GPIS_ERR_ARG; }
+    // regressObs (GPisMap3.cpp:239-256): ObsGP2D::train on the device-resident grid
+    k_obs_train<<<ctx->op.ntiles, OBS_MAXP, 0, ctx->stream>>>(d_vu, d_zinv, ctx->obs_desc, ctx->obs_tiles, ctx->op);
+    ctx->st.kernel_launches++;
+    ctx->obs_trained = true;
+    // evalPoints: centre tests, probes, numerics
+    rc = obs_test_device(ctx, d_vuv, K, d_val1, d_var1, d_tile, d_order, d_tc, d_ts, d_tcur);
+    if (rc) return rc;
+    k_frame_probes<<<(6 * K + 255) / 256, 256, 0, ctx->stream>>>(d_xl, K, P.delx, d_vup);
+    ctx->st.kernel_launches++;
+    rc = obs_test_device(ctx, d_vup, 6 * K, d_valp, d_varp, d_tile, d_order, d_tc, d_ts, d_tcur);
+    if (rc) return rc;
+    k_frame_numerics<<<(K + 255) / 256, 256, 0, ctx->stream>>>(d_xl, K, P, d_var1, d_valp, d_varp, d_st, d_grad, d_noise, d_gn);
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xyz_global, d_xg, 12ull * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, d_st, 4ull * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(grad, d_grad, 12ull * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(noise, d_noise, 4ull * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(grad_noise, d_gn, 4ull * K, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GPIS_OK;
 }

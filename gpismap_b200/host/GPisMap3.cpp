@@ -11,6 +11,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 
 #include "map_core.hpp"
@@ -68,6 +69,12 @@ struct GPisMap3::Impl {
         return core.ensure_ctx(cfg);
     }
 
+    // f-3 + f-1 on the device (gpis_frame_eval): preprocData + regressObs + the numerics of evalPoints in one call;
+    // GPIS_HOST_FRAME=1 keeps the host implementation of those steps (identical results)
+    bool device_frame = std::getenv("GPIS_HOST_FRAME") == nullptr || std::atoi(std::getenv("GPIS_HOST_FRAME")) == 0;
+    std::vector<int32_t> pre_status;
+    std::vector<float> pre_grad, pre_noise, pre_gnoise;
+    bool frameEval(float* dataz, int N, std::vector<float>& pose);
     bool preprocData(float* dataz, int N, std::vector<float>& pose);
     bool regressObs();
     void updateMapPoints();
@@ -154,6 +161,60 @@ bool GPisMap3::Impl::preprocData(float* dataz, int N, std::vector<float>& pose) 
         }
     }
     return obs_numdata > 1;
+}
+
+// ------------------------------------------------------------------ device path of Steps 0, 1 and the numerics of Step 3
+bool GPisMap3::Impl::frameEval(float* dataz, int N, std::vector<float>& pose) {
+    if (dataz == 0 || N < 1) return false;
+    obs_valid_xyzlocal.clear(); obs_valid_xyzglobal.clear();
+    obs_valid_u.clear(); obs_valid_v.clear(); obs_zinv.clear();
+    range_obs_max = 0.0f;
+    obs_numdata = 0;
+    if (pose.size() != 12) return false;
+    std::copy(pose.begin(), pose.begin() + 3, pose_tr.begin());
+    std::copy(pose.begin() + 3, pose.end(), pose_R.begin());
+    const int n = cam.width / setting.obs_skip;
+    const int m = cam.height / setting.obs_skip;
+    if (vu_grid.size() == 0) {          // GPisMap3.cpp:147-176
+        if (cam.width * cam.height != N) {
+            std::cout << "Error: The dimensions do not match!" << std::endl;
+            return false;
+        }
+        vu_grid.resize(2 * (size_t)n * m);
+        int col = 0, row = 0;
+        for (int n_ = 0; n_ < n; n_++) {
+            col = n_ * setting.obs_skip;
+            for (int m_ = 0; m_ < m; m_++) {
+                row = m_ * setting.obs_skip;
+                const int j = 2 * (m * n_ + m_);
+                vu_grid[j] = (float(row) - cam.cy) / cam.fy;
+                vu_grid[j + 1] = (float(col) - cam.cx) / cam.fx;
+            }
+        }
+        u_obs_limit[0] = -cam.cx / cam.fx;
+        u_obs_limit[1] = (float(col) - cam.cx) / cam.fx;
+        v_obs_limit[0] = -cam.cy / cam.fy;
+        v_obs_limit[1] = (float(row) - cam.cy) / cam.fy;
+    }
+    gpis_frame_params fp{};
+    fp.width = cam.width; fp.height = cam.height; fp.skip = setting.obs_skip;
+    for (int i = 0; i < 12; ++i) fp.pose[i] = pose[i];
+    fp.delx = setting.delx; fp.obs_var_thre = setting.obs_var_thre;
+    fp.min_position_noise = setting.min_position_noise; fp.min_grad_noise = setting.min_grad_noise;
+    fp.max_range = gd::kMaxRange3; fp.min_range = gd::kMinRange3;
+    const int cap = n * m;
+    obs_valid_xyzglobal.resize(3 * (size_t)cap);
+    pre_status.resize(cap); pre_grad.resize(3 * (size_t)cap); pre_noise.resize(cap); pre_gnoise.resize(cap);
+    int32_t K = 0;
+    const int rc = gpis_frame_eval(core.ctx, dataz, N, vu_grid.data(), &fp, &K, &range_obs_max, cap, obs_valid_xyzglobal.data(),
+                                   pre_status.data(), pre_grad.data(), pre_noise.data(), pre_gnoise.data());
+    if (rc != GPIS_OK) {
+        std::fprintf(stderr, "gpismap_b200: gpis_frame_eval failed (%d): %s\n", rc, gpis_last_error(core.ctx));
+        return false;
+    }
+    obs_numdata = K;
+    obs_ready = K > 1;
+    return K > 1;
 }
 
 // ------------------------------------------------------------------ regressObs (GPisMap3.cpp:239-256)
@@ -474,6 +535,27 @@ void GPisMap3::Impl::updateMapPoints() {
 void GPisMap3::Impl::evalPoints() {
     if (!core.tree || obs_numdata < 1) return;
     auto* tree = core.tree;
+    if (device_frame) {
+        // the numerics came from gpis_frame_eval; what is left is the reference's serial loop over the tree
+        std::vector<int> touched, freed;
+        ProfScope ps4(4);
+        for (int k = 0; k < obs_numdata; k++) {
+            if (pre_status[k] == 0) continue;                                    // GPisMap3.cpp:600-601
+            const int s = core.try_insert(&obs_valid_xyzglobal[3 * (size_t)k], touched);
+            if (s < 0) continue;
+            if (pre_status[k] == 1) {                                            // GPisMap3.cpp:652-655
+                freed.clear();
+                tree->remove_plain(s, freed);
+                core.drop_freed(freed);
+                continue;
+            }
+            Sample<3>& sm = tree->sample(s);
+            sm.val = -setting.fbias; sm.pose_sig = pre_noise[k]; sm.grad_sig = pre_gnoise[k];
+            sm.grad[0] = pre_grad[3 * (size_t)k]; sm.grad[1] = pre_grad[3 * (size_t)k + 1]; sm.grad[2] = pre_grad[3 * (size_t)k + 2];
+            core.activate(touched);
+        }
+        return;
+    }
     static const float Xp[6] = {1.0f, -1.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     static const float Yp[6] = {0.0f, 0.0f, 1.0f, -1.0f, 0.0f, 0.0f};
     static const float Zp[6] = {0.0f, 0.0f, 0.0f, 0.0f, 1.0f, -1.0f};
@@ -610,16 +692,26 @@ void GPisMap3::update(float* dataz, int N, std::vector<float>& pose) {
     GPisMap3Timing& T = d->timing;
     T = GPisMap3Timing{};
     double t0 = now_s();
-    const bool ok = d->preprocData(dataz, N, pose);
-    double t1 = now_s();
-    T.phase[0] = t1 - t0;
-    T.valid_pixels = d->obs_numdata;
-    if (!ok) return;
-    if (!d->ensure_ctx()) return;
-    const bool reg = d->regressObs();          // Step 1
-    double t2 = now_s();
-    T.phase[1] = t2 - t1;
-    if (!reg) return;
+    double t1, t2;
+    if (d->device_frame) {
+        if (!d->ensure_ctx()) return;
+        const bool ok = d->frameEval(dataz, N, pose);    // Steps 0 + 1 and the numerics of Step 3, on the device
+        t1 = t2 = now_s();
+        T.phase[0] = t1 - t0;
+        T.valid_pixels = d->obs_numdata;
+        if (!ok) return;
+    } else {
+        const bool ok = d->preprocData(dataz, N, pose);
+        t1 = now_s();
+        T.phase[0] = t1 - t0;
+        T.valid_pixels = d->obs_numdata;
+        if (!ok) return;
+        if (!d->ensure_ctx()) return;
+        const bool reg = d->regressObs();          // Step 1
+        t2 = now_s();
+        T.phase[1] = t2 - t1;
+        if (!reg) return;
+    }
     d->updateMapPoints();                      // Step 2
     double t3 = now_s();
     T.phase[2] = t3 - t2;

@@ -176,6 +176,29 @@ int gpis_obs_train_1d(gpis_ctx* ctx, const float* theta, const float* f, int n);
  *   reference would not evaluate, val is untouched and var = 1e6. */
 int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val_inout, float* var_inout);
 
+/* ---- one depth frame on the device (SURVEY.md 8 f-3 + f-1) --------------------------------------------------------
+ * Replaces, for GPisMap3::update, preprocData (GPisMap3.cpp:125-216), regressObs (:239-256, = gpis_obs_train_2d) and
+ * the numerics of evalPoints (:580-696): validity / inverse depth / back-projection / local->global of the
+ * sub-sampled pixels, the observation GP of the frame, then for every valid measurement the GP test at its pixel and
+ * at six finite-difference probes, occupancy values, surface normal and noise terms. What is left for the host is
+ * the serial tree insertion. Scalar types follow the reference expression by expression (the map's samples stay
+ * bit-identical to the reference's: tests/test_gpu_parity.py::test_bench_scale_map_matches_reference).
+ *   depth      N floats, metres, column-major dataz[col*height + row] (GPisMap3.cpp:183)
+ *   vu_grid    2*(width/skip)*(height/skip) floats [v,u], index (height/skip)*col_ + row_ (GPisMap3.cpp:155-170)
+ *   outputs    n_valid = valid measurements K in the reference's order; range_obs_max; per measurement k < K:
+ *              xyz_global[3], status (0 = centre test rejected: skipped; 1 = a probe rejected: inserted then removed,
+ *              :652-655; 2 = ok), grad[3] (global normal), noise, grad_noise. cap = capacity of those arrays.
+ * With K <= 1 nothing is regressed (GPisMap3.cpp:212-215). Afterwards gpis_obs_test serves this frame's GP. */
+typedef struct gpis_frame_params {
+    int32_t width, height, skip, reserved;
+    float pose[12];                 /* [t(3) | R column-major(9)], local -> global */
+    float delx, obs_var_thre, min_position_noise, min_grad_noise;
+    double max_range, min_range;    /* params.h:77-78 (4.0, 0.4) */
+} gpis_frame_params;
+int gpis_frame_eval(gpis_ctx* ctx, const float* depth, int N, const float* vu_grid, const gpis_frame_params* fp,
+                    int32_t* n_valid, float* range_obs_max, int32_t cap, float* xyz_global, int32_t* status,
+                    float* grad, float* noise, float* grad_noise);
+
 /* ---------------------------------------------------------------- replication (K5), snapshot and stats */
 /* K5 inside the library. The trained leaf table is replicated over NCCL (NVLink / NVSwitch) so that query batches can
  * be sharded over GPUs; the query path itself has no collective.

@@ -255,6 +255,89 @@ int gpis_obs_test(gpis_ctx* c, const float* xt, int d, int m, float* val, float*
     gpo_obs_test(c->obs, xt, m, val, var);
     return GPIS_OK;
 }
+// f-3 + f-1 on the CPU: the host implementation the drop-in classes used before these steps moved to the device
+// (validated bit for bit against oracle/_ref), kept here as the checker of the host-side plumbing.
+static float occ_test_h(float rinv, float rinv0, float a) {
+    return (float)(2.0 * (1.0 / (1.0 + std::exp((double)(-a * (rinv - rinv0)))) - 0.5));
+}
+static float sat_h(float v, float lo, float hi) { return std::min(std::max(v, lo), hi); }
+int gpis_frame_eval(gpis_ctx* c, const float* dataz, int N, const float* vu_grid, const gpis_frame_params* fp, int32_t* n_valid,
+                    float* range_obs_max, int32_t cap, float* xyzg, int32_t* status, float* grad_o, float* noise_o, float* gnoise_o) {
+    const int n = fp->width / fp->skip, m = fp->height / fp->skip;
+    const float* R = fp->pose + 3;
+    const float* t = fp->pose;
+    std::vector<float> zinv, vv, uu, xl;
+    float rmax = 0.f;
+    int K = 0;
+    for (int n_ = 0; n_ < n; n_++)
+        for (int m_ = 0; m_ < m; m_++) {
+            const int k = (n_ * fp->skip) * fp->height + m_ * fp->skip;
+            if ((k < N) && ((double)dataz[k] < fp->max_range) && ((double)dataz[k] > fp->min_range)) {
+                const int j = 2 * (m * n_ + m_);
+                if (rmax < dataz[k]) rmax = dataz[k];
+                zinv.push_back((float)(1.0 / (double)dataz[k]));
+                const float u = vu_grid[j + 1], v = vu_grid[j];
+                uu.push_back(u); vv.push_back(v);
+                const float xloc = u * dataz[k], yloc = v * dataz[k];
+                xl.push_back(xloc); xl.push_back(yloc); xl.push_back(dataz[k]);
+                if (K < cap && xyzg) {
+                    xyzg[3 * K] = R[0] * xloc + R[3] * yloc + R[6] * dataz[k] + t[0];
+                    xyzg[3 * K + 1] = R[1] * xloc + R[4] * yloc + R[7] * dataz[k] + t[1];
+                    xyzg[3 * K + 2] = R[2] * xloc + R[5] * yloc + R[8] * dataz[k] + t[2];
+                }
+                ++K;
+            } else zinv.push_back(-1.0f);
+        }
+    *n_valid = K; *range_obs_max = rmax;
+    if (K <= 1) return GPIS_OK;
+    if (K > cap) return GPIS_ERR_ARG;
+    gpis_obs_train_2d(c, vu_grid, zinv.data(), m, n);
+    static const float Xp[6] = {1.0f, -1.0f, 0.0f, 0.0f, 0.0f, 0.0f}, Yp[6] = {0.0f, 0.0f, 1.0f, -1.0f, 0.0f, 0.0f}, Zp[6] = {0.0f, 0.0f, 0.0f, 0.0f, 1.0f, -1.0f};
+    std::vector<float> vu(2 * (size_t)K), r0c(K, 0.f), vc(K, 0.f);
+    for (int k = 0; k < K; ++k) { vu[2 * k] = vv[k]; vu[2 * k + 1] = uu[k]; }
+    gpis_obs_test(c, vu.data(), 2, K, r0c.data(), vc.data());
+    std::vector<float> vup(12 * (size_t)K), r0p(6 * (size_t)K, 0.f), vp(6 * (size_t)K, 0.f);
+    for (int k = 0; k < K; ++k)
+        for (int i = 0; i < 6; ++i) {
+            const float X = xl[3 * k] + fp->delx * Xp[i], Y = xl[3 * k + 1] + fp->delx * Yp[i], Z = xl[3 * k + 2] + fp->delx * Zp[i];
+            vup[2 * (6 * k + i)] = Y / Z; vup[2 * (6 * k + i) + 1] = X / Z;
+        }
+    gpis_obs_test(c, vup.data(), 2, 6 * K, r0p.data(), vp.data());
+    const float w = (float)(1.0 / 6.0);
+    for (int k = 0; k < K; ++k) {
+        if (vc[k] > fp->obs_var_thre) { status[k] = 0; continue; }
+        float occ[6] = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f, -1.0f}, occ_mean = 0.0f;
+        bool failed = false;
+        for (int i = 0; i < 6; i++) {
+            if (vp[6 * k + i] > fp->obs_var_thre) { failed = true; break; }
+            const float Z = xl[3 * k + 2] + fp->delx * Zp[i];
+            occ[i] = occ_test_h((float)(1.0 / (double)Z), r0p[6 * k + i], (float)((double)Z * 30.0));
+            occ_mean += w * occ[i];
+        }
+        if (failed) { status[k] = 1; continue; }
+        float noise = 100.0f, grad_noise = 1.00f, grad[3];
+        grad[0] = (occ[0] - occ[1]) / fp->delx; grad[1] = (occ[2] - occ[3]) / fp->delx; grad[2] = (occ[4] - occ[5]) / fp->delx;
+        float norm_grad = grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2];
+        if ((double)norm_grad > 1e-6) {
+            norm_grad = std::sqrt(norm_grad);
+            const float glx = grad[0] / norm_grad, gly = grad[1] / norm_grad, glz = grad[2] / norm_grad;
+            grad[0] = R[0] * glx + R[3] * gly + R[6] * glz;
+            grad[1] = R[1] * glx + R[4] * gly + R[7] * glz;
+            grad[2] = R[2] * glx + R[5] * gly + R[8] * glz;
+            const float* p = &xl[3 * k];
+            const float dist = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+            noise = fp->min_position_noise * (sat_h(dist, 1.0f, noise));
+            grad_noise = sat_h(std::fabs(occ_mean), fp->min_grad_noise, grad_noise);
+            const float view_ang = std::max(-(p[0] * glx + p[1] * gly + p[2] * glz) / dist, (float)1e-1);
+            const float view_ang2 = view_ang * view_ang;
+            const float view_noise = (float)((double)fp->min_position_noise * ((1.0 - (double)view_ang2) / (double)view_ang2));
+            noise += view_noise;
+        }
+        grad_o[3 * k] = grad[0]; grad_o[3 * k + 1] = grad[1]; grad_o[3 * k + 2] = grad[2];
+        noise_o[k] = noise; gnoise_o[k] = grad_noise; status[k] = 2;
+    }
+    return GPIS_OK;
+}
 int gpis_get_stats(gpis_ctx* c, gpis_stats* out) {
     c->st.leaves = (int64_t)c->leaves.size();
     *out = c->st;
