@@ -20,7 +20,7 @@ EXPORTS = [
     "gpis_query", "gpis_query_device", "gpis_query_debug", "gpis_leaf_index",
     "gpis_obs_train_2d", "gpis_obs_train_1d", "gpis_obs_test",
     "gpis_get_stats", "gpis_comm_unique_id", "gpis_comm_init", "gpis_replicate",
-    "gpis_snapshot_save", "gpis_snapshot_load", "gpis_samples_set", "gpis_leaves_train_dirty", "gpis_frame_eval",
+    "gpis_snapshot_save", "gpis_snapshot_load", "gpis_samples_set", "gpis_leaves_train_dirty", "gpis_frame_eval", "gpis_reeval",
 ]
 
 

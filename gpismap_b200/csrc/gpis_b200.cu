@@ -170,6 +170,7 @@ struct gpis_ctx {
     std::vector<uint64_t> slot_key;                              // slot -> key of the leaf that owns it
     void* d_gather = nullptr; uint64_t gather_bytes = 0;         // flags, dirty list, counts, offsets
     void* d_frame = nullptr; uint64_t frame_bytes = 0;           // per-frame sensor pipeline (gpis_frame_eval)
+    void* d_reeval = nullptr; uint64_t reeval_bytes = 0;         // gpis_reeval
     QueryWork W{}; int64_t work_cap = 0;
     void* d_x = nullptr; void* d_res = nullptr; int64_t q_cap = 0;
     int32_t* d_sort = nullptr; int64_t sort_cap = 0;
@@ -429,7 +430,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->d_x); cudaFree(ctx->d_res); cudaFree(ctx->d_sort);
     cudaFree(const_cast<int4*>(ctx->prog.recs)); cudaFree(const_cast<int32_t*>(ctx->prog.off));
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
-    cudaFree(ctx->d_acc); cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt); cudaFree(ctx->d_gather); cudaFree(ctx->d_frame);
+    cudaFree(ctx->d_acc); cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt); cudaFree(ctx->d_gather); cudaFree(ctx->d_frame); cudaFree(ctx->d_reeval);
     cudaFree(ctx->d_repl); cudaFree(ctx->d_repl_idx); cudaFree(ctx->d_repl_jobs);
     if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1340,6 +1341,57 @@ int gpis_frame_eval(gpis_ctx* ctx, const float* depth, int N, const float* vu_gr
     CK(cudaMemcpyAsync(grad, d_grad, 12ull * K, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(noise, d_noise, 4ull * K, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(grad_noise, d_gn, 4ull * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPIS_OK;
+}
+
+int gpis_reeval(gpis_ctx* ctx, int n, const float* samples8, const gpis_frame_params* fp, float map_noise_param,
+                int32_t* action, float* pos_new, float* grad_new, float* noise, float* grad_noise) {
+    if (!ctx || n < 0 || !fp) return GPIS_ERR_ARG;
+    if (n == 0) return GPIS_OK;
+    if (!samples8 || !action || !pos_new || !grad_new || !noise || !grad_noise || ctx->cfg.dim != 3) return GPIS_ERR_ARG;
+    if (!ctx->obs_trained || ctx->op.d != 2) { for (int i = 0; i < n; ++i) action[i] = -1; return GPIS_OK; }
+    CK(cudaSetDevice(ctx->cfg.device));
+    ReevalParams P{};
+    for (int i = 0; i < 3; ++i) P.t[i] = fp->pose[i];
+    for (int i = 0; i < 9; ++i) P.R[i] = fp->pose[3 + i];
+    P.delx = fp->delx; P.obs_var_thre = fp->obs_var_thre; P.min_position_noise = fp->min_position_noise;
+    P.min_grad_noise = fp->min_grad_noise; P.map_noise_param = map_noise_param;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { const uint64_t r = o; o += align_up(bytes, 256); return r; };
+    const uint64_t N = (uint64_t)n;
+    const uint64_t o_smp = take(32 * N), o_loc = take(12 * N), o_vu = take(8 * N), o_val = take(4 * N), o_var = take(4 * N), o_alive = take(4 * N),
+                   o_xn = take(12 * N), o_abs = take(4 * N), o_vup = take(48 * N), o_valp = take(24 * N), o_varp = take(24 * N), o_act = take(4 * N),
+                   o_pos = take(12 * N), o_grad = take(12 * N), o_noise = take(4 * N), o_gn = take(4 * N), o_tile = take(24 * N), o_order = take(24 * N),
+                   o_tc = take(4ull * (ctx->op.ntiles + 1)), o_ts = take(4ull * (ctx->op.ntiles + 1)), o_tcur = take(4ull * (ctx->op.ntiles + 1));
+    int rc = ensure(ctx, &ctx->d_reeval, &ctx->reeval_bytes, o);
+    if (rc) return rc;
+    unsigned char* B = (unsigned char*)ctx->d_reeval;
+    float* d_smp = (float*)(B + o_smp); float* d_loc = (float*)(B + o_loc); float* d_vu = (float*)(B + o_vu);
+    float* d_val = (float*)(B + o_val); float* d_var = (float*)(B + o_var); int32_t* d_alive = (int32_t*)(B + o_alive);
+    float* d_xn = (float*)(B + o_xn); float* d_abs = (float*)(B + o_abs); float* d_vup = (float*)(B + o_vup);
+    float* d_valp = (float*)(B + o_valp); float* d_varp = (float*)(B + o_varp); int32_t* d_act = (int32_t*)(B + o_act);
+    float* d_pos = (float*)(B + o_pos); float* d_grad = (float*)(B + o_grad); float* d_noise = (float*)(B + o_noise); float* d_gn = (float*)(B + o_gn);
+    int32_t* d_tile = (int32_t*)(B + o_tile); int32_t* d_order = (int32_t*)(B + o_order);
+    int32_t* d_tc = (int32_t*)(B + o_tc); int32_t* d_ts = (int32_t*)(B + o_ts); int32_t* d_tcur = (int32_t*)(B + o_tcur);
+    CK(cudaMemcpyAsync(d_smp, samples8, 32 * N, cudaMemcpyHostToDevice, ctx->stream));
+    const int gb = (n + 255) / 256;
+    k_reeval_project<<<gb, 256, 0, ctx->stream>>>(d_smp, n, P, d_loc, d_vu);
+    ctx->st.kernel_launches++;
+    rc = obs_test_device(ctx, d_vu, n, d_val, d_var, d_tile, d_order, d_tc, d_ts, d_tcur);
+    if (rc) return rc;
+    k_reeval_walk<<<gb, 256, 0, ctx->stream>>>(d_smp, n, P, d_loc, d_val, d_var, d_alive, d_xn, d_abs, d_vup);
+    ctx->st.kernel_launches++;
+    rc = obs_test_device(ctx, d_vup, 6 * n, d_valp, d_varp, d_tile, d_order, d_tc, d_ts, d_tcur);
+    if (rc) return rc;
+    k_reeval_numerics<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_smp, n, P, d_loc, d_alive, d_xn, d_abs, d_valp, d_varp, d_act, d_pos, d_grad, d_noise, d_gn);
+    ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(action, d_act, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pos_new, d_pos, 12 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(grad_new, d_grad, 12 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(noise, d_noise, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(grad_noise, d_gn, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GPIS_OK;
 }

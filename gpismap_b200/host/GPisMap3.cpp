@@ -479,9 +479,50 @@ void GPisMap3::Impl::updateMapPoints() {
     for (const LeafHandle& h : inview) tree->collect_samples(h.cell, ids_all);
     std::vector<ReEval> st;
     std::vector<float> rinv0, var;
+    std::vector<ReOut> pre_out;
+    std::vector<int> pre_index(tree->num_samples(), -1), pre_probe;
+    if (device_frame) {
+        // projection, both observation batches and the numerics of every in-view sample on the device (gpis_reeval)
+        const int n = (int)ids_all.size();
+        std::vector<float> smp8(8 * (size_t)n), pos_new(3 * (size_t)n), grad_new(3 * (size_t)n), noise(n), gnoise(n);
+        std::vector<int32_t> act(n, -1);
+        for (int i = 0; i < n; ++i) {
+            const Sample<3>& sm = tree->sample(ids_all[i]);
+            float* o = &smp8[8 * (size_t)i];
+            o[0] = sm.pos[0]; o[1] = sm.pos[1]; o[2] = sm.pos[2];
+            o[3] = sm.grad[0]; o[4] = sm.grad[1]; o[5] = sm.grad[2];
+            o[6] = sm.pose_sig; o[7] = sm.grad_sig;
+        }
+        gpis_frame_params fp{};
+        for (int i = 0; i < 3; ++i) fp.pose[i] = pose_tr[i];
+        for (int i = 0; i < 9; ++i) fp.pose[3 + i] = pose_R[i];
+        fp.delx = setting.delx; fp.obs_var_thre = setting.obs_var_thre;
+        fp.min_position_noise = setting.min_position_noise; fp.min_grad_noise = setting.min_grad_noise;
+        {
+            ProfScope ps(0);
+            if (n > 0 && gpis_reeval(core.ctx, n, smp8.data(), &fp, setting.map_noise_param, act.data(), pos_new.data(), grad_new.data(),
+                                     noise.data(), gnoise.data()) != GPIS_OK) {
+                std::fprintf(stderr, "gpismap_b200: gpis_reeval failed: %s\n", gpis_last_error(core.ctx));
+                return;
+            }
+        }
+        st.resize(n);
+        pre_out.resize(n);
+        for (int i = 0; i < n; ++i) {
+            st[i] = ReEval{};
+            st[i].sample = ids_all[i];
+            st[i].alive1 = act[i] >= 0;
+            pre_index[ids_all[i]] = i;
+            ReOut& o = pre_out[i];
+            o.action = act[i] > 0 ? act[i] : 0;
+            for (int a = 0; a < 3; ++a) { o.pos_new[a] = pos_new[3 * (size_t)i + a]; o.grad_new[a] = grad_new[3 * (size_t)i + a]; }
+            o.noise = noise[i]; o.grad_noise = gnoise[i];
+        }
+        g_prof_s[2] += now_s() - tp0; g_prof_n[2] += 1;
+    } else {
     reeval_stage1(ids_all, st);
     reeval_stage2(st, rinv0, var);
-    std::vector<int> pre_index(tree->num_samples(), -1), pre_probe(st.size(), -1);
+    pre_probe.assign(st.size(), -1);
     {
         int probe = 0;
         for (size_t i = 0; i < st.size(); ++i) {
@@ -490,9 +531,8 @@ void GPisMap3::Impl::updateMapPoints() {
         }
     }
     g_prof_s[2] += now_s() - tp0; g_prof_n[2] += 1;
-    ProfScope ps3(3);
     // numerics of every pre-existing in-view sample, in parallel (see reeval_compute)
-    std::vector<ReOut> pre_out(st.size());
+    pre_out.resize(st.size());
     {
         const int nthr = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, (int)st.size() / 2048 + 1}));
         auto work = [&](int t) {
@@ -505,6 +545,8 @@ void GPisMap3::Impl::updateMapPoints() {
         work(0);
         for (auto& x : th) x.join();
     }
+    }
+    ProfScope ps3(3);
     // Serial pass in the reference's order. Samples created during this pass (a fused point that
     // landed in a leaf not yet visited) are evaluated on demand, leaf by leaf.
     std::vector<int> ids, fresh;

@@ -199,6 +199,16 @@ int gpis_frame_eval(gpis_ctx* ctx, const float* depth, int N, const float* vu_gr
                     int32_t* n_valid, float* range_obs_max, int32_t cap, float* xyz_global, int32_t* status,
                     float* grad, float* noise, float* grad_noise);
 
+/* The numerics of reEvalPoints (GPisMap3.cpp:321-534) for n existing samples against the current frame's observation
+ * GP: projection into the camera, first test + occupancy gate, the 10-step surface walk, six probes, fused position /
+ * normal / noises. samples8: [pos(3), grad(3), pose_sig, grad_sig] per sample. Outputs per sample: action (-1 = not
+ * re-evaluated: behind the camera, untrusted test or occupancy gate; 0 = nothing; 1 = double both noises, :451-454;
+ * 2 = replace the sample by pos_new / grad_new / noise / grad_noise). The host then removes / re-inserts in the
+ * reference's order (updateMapPoints, GPisMap3.cpp:258-319). fp->pose, delx, obs_var_thre and the noise floors are
+ * read from fp; width / height / skip / ranges are ignored. */
+int gpis_reeval(gpis_ctx* ctx, int n, const float* samples8, const gpis_frame_params* fp, float map_noise_param,
+                int32_t* action, float* pos_new, float* grad_new, float* noise, float* grad_noise);
+
 /* ---------------------------------------------------------------- replication (K5), snapshot and stats */
 /* K5 inside the library. The trained leaf table is replicated over NCCL (NVLink / NVSwitch) so that query batches can
  * be sharded over GPUs; the query path itself has no collective.

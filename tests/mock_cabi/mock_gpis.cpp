@@ -338,6 +338,134 @@ int gpis_frame_eval(gpis_ctx* c, const float* dataz, int N, const float* vu_grid
     }
     return GPIS_OK;
 }
+static void quat2dcm_h(const float q[4], float dcm[9]) {
+    dcm[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3];
+    dcm[1] = (float)(2.0 * (double)(q[1] * q[2] + q[0] * q[3]));
+    dcm[2] = (float)(2.0 * (double)(q[1] * q[3] - q[0] * q[2]));
+    dcm[3] = (float)(2.0 * (double)(q[1] * q[2] - q[0] * q[3]));
+    dcm[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3];
+    dcm[5] = (float)(2.0 * (double)(q[0] * q[1] + q[2] * q[3]));
+    dcm[6] = (float)(2.0 * (double)(q[1] * q[3] + q[0] * q[2]));
+    dcm[7] = (float)(2.0 * (double)(q[2] * q[3] - q[0] * q[1]));
+    dcm[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+}
+// reEvalPoints numerics on the CPU (the host implementation that preceded gpis_reeval; bit-exact against oracle/_ref)
+int gpis_reeval(gpis_ctx* c, int n, const float* smp, const gpis_frame_params* fp, float map_noise_param, int32_t* action,
+                float* pos_o, float* grad_o, float* noise_o, float* gnoise_o) {
+    const float* R = fp->pose + 3;
+    const float* t = fp->pose;
+    static const float Xp[6] = {1.0f, -1.0f, 0.0f, 0.0f, 0.0f, 0.0f}, Yp[6] = {0.0f, 0.0f, 1.0f, -1.0f, 0.0f, 0.0f}, Zp[6] = {0.0f, 0.0f, 0.0f, 0.0f, 1.0f, -1.0f};
+    for (int i = 0; i < n; ++i) {
+        action[i] = -1;
+        const float* s = smp + 8 * (size_t)i;
+        float loc[3];
+        loc[0] = R[0] * (s[0] - t[0]) + R[1] * (s[1] - t[1]) + R[2] * (s[2] - t[2]);
+        loc[1] = R[3] * (s[0] - t[0]) + R[4] * (s[1] - t[1]) + R[5] * (s[2] - t[2]);
+        loc[2] = R[6] * (s[0] - t[0]) + R[7] * (s[1] - t[1]) + R[8] * (s[2] - t[2]);
+        if ((double)loc[2] < 0.0) continue;
+        float vu[2] = {loc[1] / loc[2], loc[0] / loc[2]}, rinv0 = 0.f, var = 0.f;
+        gpis_obs_test(c, vu, 2, 1, &rinv0, &var);
+        if (var > fp->obs_var_thre) continue;
+        const float z_loc = loc[2];
+        float oc = occ_test_h((float)(1.0 / (double)z_loc), rinv0, (float)((double)z_loc * 30.0));
+        if ((double)oc < -0.02) continue;
+        float gl[3];
+        gl[0] = R[0] * s[3] + R[1] * s[4] + R[2] * s[5];
+        gl[1] = R[3] * s[3] + R[4] * s[4] + R[5] * s[5];
+        gl[2] = R[6] * s[3] + R[7] * s[4] + R[8] * s[5];
+        float abs_oc = (float)std::fabs((double)oc), dx = fp->delx;
+        float xn[3] = {loc[0], loc[1], loc[2]};
+        for (int it = 0; it < 10 && (double)abs_oc > 0.02; it++) {
+            if (oc < 0) { xn[0] += gl[0] * dx; xn[1] += gl[1] * dx; xn[2] += gl[2] * dx; }
+            else        { xn[0] -= gl[0] * dx; xn[1] -= gl[1] * dx; xn[2] -= gl[2] * dx; }
+            const float r_new = z_loc;
+            const float oc_new = occ_test_h((float)(1.0 / (double)r_new), rinv0, (float)((double)r_new * 30.0));
+            const float abs_oc_new = (float)std::fabs((double)oc_new);
+            if ((double)abs_oc_new < 0.02 || (double)oc < -0.02) break;
+            else if ((double)(oc * oc_new) < 0.0) dx = (float)(0.5 * (double)dx);
+            else dx = (float)(1.1 * (double)dx);
+            abs_oc = abs_oc_new;
+            oc = oc_new;
+        }
+        float vup[12], r0p[6] = {0}, vp[6] = {0};
+        for (int p = 0; p < 6; ++p) {
+            const float X = xn[0] + fp->delx * Xp[p], Y = xn[1] + fp->delx * Yp[p], Z = xn[2] + fp->delx * Zp[p];
+            vup[2 * p] = Y / Z; vup[2 * p + 1] = X / Z;
+        }
+        gpis_obs_test(c, vup, 2, 6, r0p, vp);
+        action[i] = 0;
+        const float w = (float)(1.0 / 6.0);
+        float occ[6] = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f, -1.0f}, occ_mean = 0.0f, r0_mean = 0.0f, r0_sqr_sum = 0.0f, r_new = loc[2], last_var = 0.f;
+        for (int p = 0; p < 6; p++) {
+            const float Z = xn[2] + fp->delx * Zp[p];
+            r_new = Z; last_var = vp[p];
+            if (vp[p] > fp->obs_var_thre) break;
+            occ[p] = occ_test_h((float)(1.0 / (double)r_new), r0p[p], (float)((double)r_new * 30.0));
+            occ_mean += w * occ[p];
+            const float r0 = (float)(1.0 / (double)r0p[p]);
+            r0_sqr_sum += r0 * r0; r0_mean += w * r0;
+        }
+        if (last_var > fp->obs_var_thre) continue;
+        const float pos[3] = {s[0], s[1], s[2]}, grad[3] = {s[3], s[4], s[5]};
+        float gnl[3] = {(occ[0] - occ[1]) / fp->delx, (occ[2] - occ[3]) / fp->delx, (occ[4] - occ[5]) / fp->delx};
+        const float norm = std::sqrt(gnl[0] * gnl[0] + gnl[1] * gnl[1] + gnl[2] * gnl[2]);
+        if ((double)norm < 1e-3) { action[i] = 1; continue; }
+        float r_var = (float)((double)r0_sqr_sum / 5.0 - (double)(r0_mean * r0_mean) * 6.0 / 5.0);
+        r_var /= fp->delx;
+        float noise = 100.0f, grad_noise = 1.0f;
+        if ((double)norm > 1e-6) {
+            gnl[0] = gnl[0] / norm; gnl[1] = gnl[1] / norm; gnl[2] = gnl[2] / norm;
+            noise = fp->min_position_noise * sat_h(r_new * r_new, 1.0f, noise);
+            grad_noise = sat_h(std::fabs(occ_mean) + r_var, fp->min_grad_noise, grad_noise);
+        } else noise = fp->min_position_noise * noise;
+        const float dist = std::sqrt(xn[0] * xn[0] + xn[1] * xn[1] + xn[2] * xn[2]);
+        const float view_ang = std::max(-(xn[0] * gnl[0] + xn[1] * gnl[1] + xn[2] * gnl[2]) / dist, (float)1e-1);
+        const float view_ang2 = view_ang * view_ang;
+        const float view_noise = (float)((double)fp->min_position_noise * ((1.0 - (double)view_ang2) / (double)view_ang2));
+        noise += view_noise + abs_oc;
+        grad_noise = (float)((double)grad_noise + 0.1 * (double)view_noise);
+        float pn[3], gn[3];
+        pn[0] = R[0] * xn[0] + R[3] * xn[1] + R[6] * xn[2] + t[0];
+        pn[1] = R[1] * xn[0] + R[4] * xn[1] + R[7] * xn[2] + t[1];
+        pn[2] = R[2] * xn[0] + R[5] * xn[1] + R[8] * xn[2] + t[2];
+        gn[0] = R[0] * gnl[0] + R[3] * gnl[1] + R[6] * gnl[2];
+        gn[1] = R[1] * gnl[0] + R[4] * gnl[1] + R[7] * gnl[2];
+        gn[2] = R[2] * gnl[0] + R[5] * gnl[1] + R[8] * gnl[2];
+        const float noise_old = s[6], gno = s[7], pns = noise_old + noise, gns = gno + grad_noise;
+        if ((double)gno > 0.5 || (double)gno > 0.6) {
+            ;
+        } else {
+            pn[0] = (noise * pos[0] + noise_old * pn[0]) / pns;
+            pn[1] = (noise * pos[1] + noise_old * pn[1]) / pns;
+            pn[2] = (noise * pos[2] + noise_old * pn[2]) / pns;
+            const float d2 = (pos[0] - pn[0]) * (pos[0] - pn[0]) + (pos[1] - pn[1]) * (pos[1] - pn[1]) + (pos[2] - pn[2]) * (pos[2] - pn[2]);
+            const float dist2 = (float)(0.5 * (double)std::sqrt(d2));
+            float axis[3];
+            axis[0] = gn[1] * grad[2] - gn[2] * grad[1];
+            axis[1] = -gn[0] * grad[2] + gn[2] * grad[0];
+            axis[2] = gn[0] * grad[1] - gn[1] * grad[0];
+            float ang = (float)std::acos((double)(gn[0] * grad[0] + gn[1] * grad[1] + gn[2] * grad[2]));
+            ang = ang * noise / pns;
+            float q[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+            if (ang > 1 - 6) {
+                q[0] = (float)std::cos((double)ang / 2.0);
+                const float sina = (float)std::sin((double)ang / 2.0);
+                q[1] = axis[0] * sina; q[2] = axis[1] * sina; q[3] = axis[2] * sina;
+            }
+            float Rot[9];
+            quat2dcm_h(q, Rot);
+            gn[0] = Rot[0] * grad[0] + Rot[1] * grad[1] + Rot[2] * grad[2];
+            gn[1] = Rot[3] * grad[0] + Rot[4] * grad[1] + Rot[5] * grad[2];
+            gn[2] = Rot[6] * grad[0] + Rot[7] * grad[1] + Rot[8] * grad[2];
+            grad_noise = std::min((float)1.0, std::max(grad_noise * gno / gns + dist2, map_noise_param));
+            noise = std::max((noise * noise_old / pns + dist2), map_noise_param);
+        }
+        action[i] = 2;
+        for (int a = 0; a < 3; ++a) { pos_o[3 * (size_t)i + a] = pn[a]; grad_o[3 * (size_t)i + a] = gn[a]; }
+        noise_o[i] = noise; gnoise_o[i] = grad_noise;
+    }
+    return GPIS_OK;
+}
 int gpis_get_stats(gpis_ctx* c, gpis_stats* out) {
     c->st.leaves = (int64_t)c->leaves.size();
     *out = c->st;
