@@ -272,12 +272,12 @@ def main():
         s = ctx.stats()
         return s["last_query_ms"], s
 
+    sampler = ClockSampler(local)
+    sampler.start()          # started before the warm-up: at 8 GPUs the timed region alone is shorter than nvidia-smi's start-up
     for _ in range(args.warmup):
         step_device()
     sync_all()
     launches0 = ctx.stats()["kernel_launches"]
-    sampler = ClockSampler(local)
-    sampler.start()
     ms_steps, eval_ms_steps = [], []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
