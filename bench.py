@@ -342,14 +342,16 @@ def main():
         fp32_peak = props.multi_processor_count * 128 * 2 * sm_clock / 1e12
         fp32_ach = sq["last_query_flops"] / eval_s / 1e12 if eval_s > 0 else 0.0
         # DRAM traffic of the evaluation kernels for this exact workload, from the committed ncu capture
-        # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over one step's launches)
+        # (profiles/rNN_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over one step's launches)
         traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tj.get("grid") == args.grid and tj.get("frames") == args.frames and world == 1:
-                traffic = float(tj["dram_bytes_per_step"])
-        except (OSError, ValueError, KeyError):
-            traffic = None
+        for tag in ("r02", "r01"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")))
+                if tj.get("grid") == args.grid and tj.get("frames") == args.frames and world == 1 and args.rtimes == 2.0:
+                    traffic = float(tj["dram_bytes_per_step"])
+                    break
+            except (OSError, ValueError, KeyError):
+                continue
         out = {
             "metric": "sdf_grad_var_queries_per_s", "value": total_q / (ms_all * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all,

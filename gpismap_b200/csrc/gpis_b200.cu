@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
 #include <nccl.h>   // types only: the library is resolved at run time (gpis_comm_init), there is no link dependency
 
 #include <algorithm>
@@ -199,6 +200,12 @@ struct gpis_ctx {
     void* d_repl_jobs = nullptr; uint64_t repl_jobs_cap = 0;
     gpis_stats st{};
     int eval_version = 3;
+};
+
+// NVTX range per C-ABI call / phase (the reference has no tracing at all)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 #define CK(call)                                                                                   \
@@ -612,6 +619,7 @@ int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
 // job order) receives the non-positive-pivot counts.
 static int train_jobs(gpis_ctx* ctx, std::vector<TrainJob>& jobs, const float* d_smp, int maxN, int maxnb,
                       int32_t* status_host, float* ms_out) {
+    NvtxRange nvtx_("K1 leaf train");
     *ms_out = 0.f;
     if (jobs.empty()) return 0;
     std::vector<int> order(jobs.size());
@@ -642,6 +650,7 @@ static int train_jobs(gpis_ctx* ctx, std::vector<TrainJob>& jobs, const float* d
 
 int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres,
                        const int32_t* offsets, const float* samples, int32_t* status) {
+    NvtxRange nvtx_("gpis_leaves_update");
     if (!ctx || n_leaves < 0) return GPIS_ERR_ARG;
     if (n_leaves == 0) return GPIS_OK;
     if (!cells || !centres || !offsets || !samples) return GPIS_ERR_ARG;
@@ -759,6 +768,7 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
 // ------------------------------------------------------------------ f-2: device sample store + device-side gather
 int gpis_samples_set(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres, const int32_t* offsets,
                      const float* samples) {
+    NvtxRange nvtx_("gpis_samples_set");
     if (!ctx || n_leaves < 0) return GPIS_ERR_ARG;
     if (n_leaves == 0) return GPIS_OK;
     if (!cells || !centres || !offsets || (offsets[n_leaves] > 0 && !samples)) return GPIS_ERR_ARG;
@@ -812,6 +822,7 @@ int gpis_samples_set(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const fl
 }
 
 int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_cells, float radius, int32_t* n_trained) {
+    NvtxRange nvtx_("gpis_leaves_train_dirty");
     if (!ctx || n_active < 0 || !(radius > 0.f)) return GPIS_ERR_ARG;
     if (n_trained) *n_trained = 0;
     ctx->st.last_train_leaves = 0; ctx->st.last_train_ms = 0.f; ctx->st.last_train_skipped = 0;
@@ -977,6 +988,7 @@ int gpis_leaf_get(gpis_ctx* ctx, const int32_t* cell, int32_t* N, int32_t* ng, f
 
 // ------------------------------------------------------------------ queries
 static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, int32_t* h_chosen, int32_t* h_tie) {
+    NvtxRange nvtx_("gpis_query: candidates + eval + fuse");
     const int dim = ctx->cfg.dim;
     const int64_t CH = 1 << 22;  // queries per chunk (bounds scratch: ~160 B/query)
     const int64_t chunk_cap = std::min<int64_t>(n, CH);
@@ -1068,6 +1080,7 @@ int gpis_query_device(gpis_ctx* ctx, const float* x_device, int64_t n, float* re
 }
 
 static int query_host(gpis_ctx* ctx, const float* x, int64_t n, float* res, int32_t* chosen, int32_t* tie) {
+    NvtxRange nvtx_("gpis_query (host buffers)");
     if (!ctx || !x || !res || n < 1) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     const int dim = ctx->cfg.dim, w2 = 2 * (1 + dim);
@@ -1148,6 +1161,7 @@ static int obs_partition_2d(gpis_ctx* ctx, const float* vu, int ni, int nj) {
 }
 
 int gpis_obs_train_2d(gpis_ctx* ctx, const float* vu, const float* zinv, int ni, int nj) {
+    NvtxRange nvtx_("gpis_obs_train_2d");
     if (!ctx) return GPIS_ERR_ARG;
     if (!vu || !zinv || ni <= 0 || nj <= 0) return GPIS_OK;   // ObsGP.cpp:333: silently untrained
     CK(cudaSetDevice(ctx->cfg.device));
@@ -1169,6 +1183,7 @@ int gpis_obs_train_2d(gpis_ctx* ctx, const float* vu, const float* zinv, int ni,
 }
 
 int gpis_obs_train_1d(gpis_ctx* ctx, const float* theta, const float* f, int N) {
+    NvtxRange nvtx_("gpis_obs_train_1d");
     if (!ctx) return GPIS_ERR_ARG;
     if (!theta || !f || N <= 0) return GPIS_OK;                // ObsGP.cpp:89
     CK(cudaSetDevice(ctx->cfg.device));
@@ -1234,6 +1249,7 @@ static int obs_test_device(gpis_ctx* ctx, const float* d_x, int m, float* d_val,
 }
 
 int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, float* var) {
+    NvtxRange nvtx_("gpis_obs_test");
     if (!ctx || !xt || !val || !var || m < 0) return GPIS_ERR_ARG;
     if (m == 0) return GPIS_OK;
     if (!ctx->obs_trained) return GPIS_OK;                    // ObsGP.cpp:147-149, 412-414: outputs untouched
@@ -1267,6 +1283,7 @@ int gpis_obs_test(gpis_ctx* ctx, const float* xt, int d, int m, float* val, floa
 int gpis_frame_eval(gpis_ctx* ctx, const float* depth, int N, const float* vu_grid, const gpis_frame_params* fp,
                     int32_t* n_valid, float* range_obs_max, int32_t cap, float* xyz_global, int32_t* status,
                     float* grad, float* noise, float* grad_noise) {
+    NvtxRange nvtx_("gpis_frame_eval");
     if (!ctx || !depth || !vu_grid || !fp || !n_valid || !range_obs_max || N < 1) return GPIS_ERR_ARG;
     if (ctx->cfg.dim != 3 || fp->skip < 1) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
@@ -1347,6 +1364,7 @@ int gpis_frame_eval(gpis_ctx* ctx, const float* depth, int N, const float* vu_gr
 
 int gpis_reeval(gpis_ctx* ctx, int n, const float* samples8, const gpis_frame_params* fp, float map_noise_param,
                 int32_t* action, float* pos_new, float* grad_new, float* noise, float* grad_noise) {
+    NvtxRange nvtx_("gpis_reeval");
     if (!ctx || n < 0 || !fp) return GPIS_ERR_ARG;
     if (n == 0) return GPIS_OK;
     if (!samples8 || !action || !pos_new || !grad_new || !noise || !grad_noise || ctx->cfg.dim != 3) return GPIS_ERR_ARG;
@@ -1613,6 +1631,7 @@ static int receive_install(gpis_ctx* ctx, const ReplHeader& hd, const std::vecto
 extern "C" {
 
 int gpis_replicate(gpis_ctx* ctx, int root) {
+    NvtxRange nvtx_("gpis_replicate");
     if (!ctx) return GPIS_ERR_ARG;
     if (!ctx->comm) { ctx->err = "gpis_replicate before gpis_comm_init"; return GPIS_ERR_STATE; }
     if (root < 0 || root >= ctx->comm_world) return GPIS_ERR_ARG;
@@ -1669,6 +1688,7 @@ int gpis_replicate(gpis_ctx* ctx, int root) {
 // The reference has no persistence (its map dies with the process, GPisMap3.cpp:951-972 only lists points); this
 // gives the trained device map checkpoint/resume and a wire format a replica can be started from.
 int gpis_snapshot_save(gpis_ctx* ctx, const char* path) {
+    NvtxRange nvtx_("gpis_snapshot_save");
     if (!ctx || !path) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     std::FILE* f = std::fopen(path, "wb");
@@ -1693,6 +1713,7 @@ int gpis_snapshot_save(gpis_ctx* ctx, const char* path) {
 }
 
 int gpis_snapshot_load(gpis_ctx* ctx, const char* path) {
+    NvtxRange nvtx_("gpis_snapshot_load");
     if (!ctx || !path) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     std::FILE* f = std::fopen(path, "rb");

@@ -1,7 +1,7 @@
 """Turn the raw outputs of scripts/collect_evidence.sh (gpurun_out/) into the committed summaries under profiles/."""
 import collections, csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 def short(name):
@@ -51,7 +51,7 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
         "lts__t_bytes.sum", "smsp__inst_executed.sum", "smsp__average_warps_issue_stalled", "sm__sass_inst_executed_op_shared"]
-for kern in ("k_eval_v3", "k_leaf_train"):
+for kern in ("k_eval_v3", "k_leaf_train", "other"):
     rep = os.path.join(G, f"{R}_{kern}.ncu-rep")
     if not os.path.exists(rep): continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -65,5 +65,6 @@ for kern in ("k_eval_v3", "k_leaf_train"):
                 if any(h.startswith(w) for w in want):
                     f.write(f"  {h:86s} {r[i]} {units[i]}\n")
     print("wrote", f"{R}_{kern}_ncu_full.txt")
-for fn in (f"{R}_bench.json", f"{R}_bench_reference.json"):
-    shutil.copy(os.path.join(G, fn), os.path.join(P, fn))
+for fn in (f"{R}_bench.json", f"{R}_bench_reference.json", f"{R}_hbm_regime.json", f"{R}_update_profile.txt", f"{R}_train_bench.txt"):
+    if os.path.exists(os.path.join(G, fn)):
+        shutil.copy(os.path.join(G, fn), os.path.join(P, fn))
