@@ -7,8 +7,7 @@ from gpismap_b200 import cabi
 import helpers
 rng = np.random.default_rng(5)
 nleaf = int(sys.argv[1]) if len(sys.argv) > 1 else 296
-tv = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-print("training kernel version", tv, "leaves per launch", nleaf)
+print("k_leaf_train (with the refinement step), leaves per launch", nleaf)
 sizes = tuple(int(v) for v in os.environ.get("TB_SIZES", "48,96,144,200,260,330,400,480").split(","))
 for N in sizes:
     ctx = cabi.Ctx(dim=3)
@@ -30,10 +29,5 @@ for N in sizes:
         tb = np.zeros(8, np.int64); cabi.lib().gpis_debug_train_timing(tb.ctypes.data_as(C.c_void_p))
         tot = max(1, tb[:5].sum())
         print("   phases A/B/C/D/E %:", " ".join(f"{100 * v / tot:5.1f}" for v in tb[:5]), " cycles/launch", int(tot // 3))
-    if hasattr(cabi.lib(), "gpis_debug_train2_timing") and tv == 2:
-        import ctypes as C
-        tb = np.zeros(16, np.int64); cabi.lib().gpis_debug_train2_timing(tb.ctypes.data_as(C.c_void_p))
-        tot = max(1, tb[:7].sum())
-        print("   v2 phases A+B / prologue / k-loop / drain / diag / rows / D %:", " ".join(f"{100 * v / tot:5.1f}" for v in tb[:7]), " cycles/leaf-CTA", int(tot // 3 // max(1, (nleaf + 295) // 296)))
     print(f"N={N:4d} n={n:5d} nb={(n + 31) // 32:3d}  {min(ts):8.3f} ms  {fl / min(ts) / 1e9:8.1f} TFLOP/s")
     del ctx

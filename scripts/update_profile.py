@@ -5,10 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gpismap_b200 import hostapi, synth
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-tv = int(sys.argv[2]) if len(sys.argv) > 2 else 2          # training kernel version (gpis_set_train_version)
 m = hostapi.GPisMap3()
-from gpismap_b200 import cabi
-print("training kernel version", tv)
 rows = []
 for k in range(nf):
     dz, pose = synth.frame(k, nf)
@@ -25,7 +22,7 @@ print("median / p90 / max over", nf, "frames (ms)")
 for i, n in enumerate(names):
     print(f"{n:18s} {np.median(a[:, i]):10.2f} {np.percentile(a[:, i], 90):10.2f} {a[:, i].max():10.2f}")
 
-pn = ["gpis_obs_test", "uMP: cull", "uMP: collect+stage (incl obs)", "uMP: serial apply (incl obs)", "evalPoints: serial insert", "train: dirty set", "train: gather", "gpis_leaves_update", "sync_table"]
+pn = ["gpis_obs_test / gpis_reeval", "uMP: cull", "uMP: collect + gpis_reeval", "uMP: serial apply (incl on-demand obs tests)", "evalPoints: serial insert", "train: dirty set (host path)", "train: sample lists (gpis_samples_set)", "gpis_leaves_train_dirty / _update", "sync_table"]
 print("host profile, ms per frame (calls per frame)")
 for i, n in enumerate(pn):
     print(f"{n:32s} {secs[i] * 1e3 / nf:9.2f}  ({calls[i] / nf:.1f})")
