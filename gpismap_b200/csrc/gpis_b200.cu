@@ -403,6 +403,14 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
                      cfg->device, prop.major, prop.minor);
         return GPIS_ERR_NODEVICE;
     }
+    {   // the exact-tie replay keeps at most GPIS_MAXC candidates per query (query.cuh): refuse a search box that can exceed it
+        const double per_axis = 2.0 * std::ceil((double)cfg->search_half / (2.0 * (double)cfg->cluster_half)) + 2.0;
+        if (!(cfg->cluster_half > 0.f) || !(cfg->search_half > 0.f) || std::pow(per_axis, cfg->dim) > GPIS_MAXC) {
+            std::fprintf(stderr, "gpis_b200: search_half / cluster_half = %g gives up to %g candidate leaves per query; the limit is %d\n",
+                         (double)cfg->search_half / (double)cfg->cluster_half, std::pow(per_axis, cfg->dim), GPIS_MAXC);
+            return GPIS_ERR_ARG;
+        }
+    }
     gpis_ctx* ctx = new gpis_ctx();
     ctx->cfg = *cfg;
     if (ctx->cfg.arena_chunk_bytes < (64ull << 20)) ctx->cfg.arena_chunk_bytes = 64ull << 20;

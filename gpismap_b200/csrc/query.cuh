@@ -137,6 +137,44 @@ __device__ inline void ssr_insertion_sort(CandList& L, int first, int last) {
         } else ssr_unguarded_linear_insert(L, i);
     }
 }
+// heapsort fallback of introsort (depth limit reached): __partial_sort(first, last, last) = __make_heap + __sort_heap
+// (bits/stl_heap.h: __adjust_heap, __push_heap, __pop_heap), replayed move by move
+__device__ inline void ssr_adjust_heap(CandList& L, int first, int hole, int len, float vk, int vs) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (L.key[first + child] < L.key[first + child - 1]) child--;
+        L.key[first + hole] = L.key[first + child]; L.slot[first + hole] = L.slot[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        L.key[first + hole] = L.key[first + child - 1]; L.slot[first + hole] = L.slot[first + child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && L.key[first + parent] < vk) {
+        L.key[first + hole] = L.key[first + parent]; L.slot[first + hole] = L.slot[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    L.key[first + hole] = vk; L.slot[first + hole] = vs;
+}
+__device__ inline void ssr_heapsort(CandList& L, int first, int last) {
+    const int len = last - first;
+    if (len >= 2)
+        for (int parent = (len - 2) / 2;; --parent) {
+            ssr_adjust_heap(L, first, parent, len, L.key[first + parent], L.slot[first + parent]);
+            if (parent == 0) break;
+        }
+    for (int end = last; end - first > 1;) {
+        --end;
+        const float vk = L.key[end]; const int vs = L.slot[end];
+        L.key[end] = L.key[first]; L.slot[end] = L.slot[first];
+        ssr_adjust_heap(L, first, 0, end - first, vk, vs);
+    }
+}
 __device__ inline void std_sort_replay(CandList& L, int n) {
     if (n <= 1) return;
     int lg = 0;
@@ -150,7 +188,7 @@ __device__ inline void std_sort_replay(CandList& L, int n) {
         // the reference recurses into [cut, last) FIRST and then continues with [first, cut):
         // the two sub-ranges are disjoint, so the order of processing does not change the result.
         while (last - first > 16) {
-            if (depth == 0) { ssr_insertion_sort(L, first, last); break; }
+            if (depth == 0) { ssr_heapsort(L, first, last); break; }
             --depth;
             const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
             int med;

@@ -327,8 +327,9 @@ void gpo_map_free(gpo_map* m) {
  * bits/stl_algo.h (GCC 13): __sort -> __introsort_loop (median-of-3 to first, unguarded partition,
  * threshold 16, depth limit 2*floor(log2 n), heapsort fallback) -> __final_insertion_sort.
  * Sorts the parallel arrays (idx, key) by key with comparator key[a] < key[b]; the arrays start in
- * the tree's DFS order. The heapsort fallback needs > 2 log2(n) bad partitions and does not occur
- * for n <= 256 candidate lists; if it ever did, the remaining range is finished by insertion. */
+ * the tree's DFS order. The heapsort fallback (__partial_sort = __heap_select + __sort_heap, bits/stl_heap.h) is
+ * replayed too: it needs > 2 log2(n) bad partitions, which natural candidate lists do not produce, but an adversarial
+ * one can (tests/test_oracle_vs_ref.py builds one with McIlroy's adversary against the real std::sort). */
 static void ssr_swap(int* idx, float* key, int a, int b) {
     int ti = idx[a]; idx[a] = idx[b]; idx[b] = ti;
     float tk = key[a]; key[a] = key[b]; key[b] = tk;
@@ -349,9 +350,50 @@ static void ssr_insertion_sort(int* idx, float* key, int first, int last) {
         } else ssr_unguarded_linear_insert(idx, key, i);
     }
 }
+/* __adjust_heap + __push_heap (bits/stl_heap.h) on the range starting at `first` */
+static void ssr_adjust_heap(int* idx, float* key, int first, int hole, int len, int vi, float vk) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (key[first + child] < key[first + child - 1]) child--;
+        idx[first + hole] = idx[first + child]; key[first + hole] = key[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        idx[first + hole] = idx[first + child - 1]; key[first + hole] = key[first + child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && key[first + parent] < vk) {
+        idx[first + hole] = idx[first + parent]; key[first + hole] = key[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    idx[first + hole] = vi; key[first + hole] = vk;
+}
+/* __partial_sort(first, last, last): __make_heap, then __sort_heap by repeated __pop_heap */
+static int g_heapsort_calls = 0;   /* test hook: how often the depth limit tripped */
+int gpo_sort_replay_heapsorts(void) { return g_heapsort_calls; }
+static void ssr_heapsort(int* idx, float* key, int first, int last) {
+    const int len = last - first;
+    ++g_heapsort_calls;
+    if (len >= 2)
+        for (int parent = (len - 2) / 2;; --parent) {
+            ssr_adjust_heap(idx, key, first, parent, len, idx[first + parent], key[first + parent]);
+            if (parent == 0) break;
+        }
+    for (int end = last; end - first > 1;) {
+        --end;
+        const int vi = idx[end]; const float vk = key[end];
+        idx[end] = idx[first]; key[end] = key[first];
+        ssr_adjust_heap(idx, key, first, 0, end - first, vi, vk);
+    }
+}
 static void ssr_introsort_loop(int* idx, float* key, int first, int last, int depth) {
     while (last - first > 16) {
-        if (depth == 0) { ssr_insertion_sort(idx, key, first, last); return; }
+        if (depth == 0) { ssr_heapsort(idx, key, first, last); return; }
         --depth;
         /* __move_median_to_first(first, first+1, mid, last-1) */
         const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
@@ -384,6 +426,14 @@ static void std_sort_replay(int* idx, float* key, int n) {
         ssr_insertion_sort(idx, key, 0, 16);
         for (int i = 16; i != n; ++i) ssr_unguarded_linear_insert(idx, key, i);
     } else ssr_insertion_sort(idx, key, 0, n);
+}
+
+/* test hook: the replay on its own (idx starts as 0..n-1) */
+void gpo_sort_replay(const float* keys, int n, int* idx_out) {
+    float* k = (float*)malloc(sizeof(float) * (n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) { idx_out[i] = i; k[i] = keys[i]; }
+    std_sort_replay(idx_out, k, n);
+    free(k);
 }
 
 /* One query: GPisMap3.cpp:803-900 / GPisMap.cpp:673-761. Geometry is always fp32 (it decides

@@ -84,6 +84,9 @@ int gpo_obs_bounds(const gpo_obs* o, float* bi, float* bj); /* returns nbi*65536
  * reference would not evaluate (cpp/src/ObsGP.cpp:363-377, 396-403, 152-186). */
 void gpo_obs_test(const gpo_obs* o, const float* xt, int m, real* val, real* var);
 
+void gpo_sort_replay(const float* keys, int n, int* idx_out);
+int gpo_sort_replay_heapsorts(void);
+
 #ifdef __cplusplus
 }
 #endif

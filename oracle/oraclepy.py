@@ -50,6 +50,8 @@ class Oracle:
             "gpo_map_create": (vp, [C.c_int, C.c_int, fp, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp]),
             "gpo_map_free": (None, [vp]),
             "gpo_map_test": (None, [vp, fp, C.c_int, rp, vp, vp]),
+            "gpo_sort_replay": (None, [fp, C.c_int, ip]),
+            "gpo_sort_replay_heapsorts": (C.c_int, []),
             "gpo_obs2d_train": (vp, [fp, fp, C.c_int, C.c_int]),
             "gpo_obs1d_train": (vp, [fp, fp, C.c_int]),
             "gpo_obs_free": (None, [vp]),
@@ -77,6 +79,12 @@ class Oracle:
     # ---------------------------------------------------------------- leaf GP
     def gp_train(self, dim, samples, scale, noise):
         return OracleGP(self, dim, samples, scale, noise)
+
+    def sort_replay(self, keys):
+        k = np.ascontiguousarray(keys, np.float32).ravel()
+        idx = np.zeros(k.size, np.int32)
+        self.L.gpo_sort_replay(k, k.size, idx)
+        return idx
 
     def make_map(self, dim, centres, cluster_half, gps, search_half, var_thre, noise, boxes=None):
         return OracleMap(self, dim, centres, cluster_half, gps, search_half, var_thre, noise, boxes)

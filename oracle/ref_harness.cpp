@@ -71,6 +71,29 @@ const float HUGE_HALF = 1.0e6f;
 
 extern "C" {
 
+// The sort the reference runs on its candidate lists (GPisMap3.cpp:826-829: std::sort of an index array with the
+// comparator sqdst[i1] < sqdst[i2]), on its own: the pin for the oracle's move-by-move replay.
+void ref_std_sort_indices(const float* keys, int n, int* idx) {
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::sort(idx, idx + n, [&](int a, int b) { return keys[a] < keys[b]; });
+}
+// McIlroy's adversary ("A killer adversary for quicksort", 1999) run against this libstdc++'s std::sort: produces
+// keys for which the introsort's partitions are as bad as possible, so that its depth limit trips and the heapsort
+// fallback runs. keys_out receives a permutation-like array of n distinct values.
+void ref_std_sort_killer(int n, int ties, float* keys_out) {   // ties > 1: the comparator sees val / ties, so exact ties occur
+    std::vector<int> val(n), idx(n);
+    if (ties < 1) ties = 1;
+    const int gas = n;
+    int nsolid = 0, candidate = 0;
+    for (int i = 0; i < n; ++i) { val[i] = gas; idx[i] = i; }
+    std::sort(idx.begin(), idx.end(), [&](int x, int y) {
+        if (val[x] == gas && val[y] == gas) { if (x == candidate) val[x] = nsolid++; else val[y] = nsolid++; }
+        if (val[x] == gas) candidate = x;
+        else if (val[y] == gas) candidate = y;
+        return val[x] / ties < val[y] / ties;
+    });
+    for (int i = 0; i < n; ++i) keys_out[i] = (float)((val[i] == gas ? nsolid++ : val[i]) / ties);
+}
 int ref_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
 
 // ------------------------------------------------------------------ covariance functions

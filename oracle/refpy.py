@@ -45,6 +45,8 @@ def lib():
         vp = C.c_void_p
         sig = {
             "ref_hardware_concurrency": (C.c_int, []),
+            "ref_std_sort_indices": (None, [f32p, C.c_int, i32p]),
+            "ref_std_sort_killer": (None, [C.c_int, C.c_int, f32p]),
             "ref_matern_train": (C.c_int, [C.c_int, f32p, f32p, C.c_int, C.c_float, f32p, f32p, f32p, C.c_int]),
             "ref_matern_test": (C.c_int, [C.c_int, f32p, f32p, C.c_int, f32p, C.c_int, C.c_float, f32p, C.c_int]),
             "ref_ou_train": (None, [C.c_int, f32p, C.c_int, C.c_float, C.c_float, f32p]),
@@ -118,6 +120,21 @@ def _ptr(a):
 
 def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def std_sort_indices(keys):
+    """std::sort of 0..n-1 by keys[a] < keys[b] with the libstdc++ the reference was built with."""
+    k = f32(keys).ravel()
+    idx = np.zeros(k.size, np.int32)
+    lib().ref_std_sort_indices(k, k.size, idx)
+    return idx
+
+
+def std_sort_killer(n, ties=1):
+    """Keys that drive this std::sort into its heapsort fallback (McIlroy's adversary); ties > 1 makes groups of equal keys."""
+    k = np.zeros(n, np.float32)
+    lib().ref_std_sort_killer(n, ties, k)
+    return k
 
 
 class RefGP:

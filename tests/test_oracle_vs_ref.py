@@ -73,3 +73,31 @@ def test_map_query(ref, oracle, dim):
     nc = np.array([M.candidates(q, P["search"])[0].shape[0] for q in x])
     assert np.array_equal(chosen[:, 0], nc)
     assert np.array_equal(got, want)
+
+
+def test_std_sort_replay_matches_libstdcxx_including_heapsort_fallback(ref, oracle):
+    """The candidate order is whatever libstdc++'s std::sort leaves (GPisMap3.cpp:826-829): not stable, so exact ties
+    are ordered by its partitioning. The oracle (and the CUDA kernel, same code) replays it move by move; here the
+    replay is pinned against the real std::sort on tie-heavy random keys, on sorted / reversed / organ-pipe inputs and
+    on McIlroy-adversary inputs that push the introsort past its depth limit into the heapsort fallback."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for n in (1, 2, 3, 16, 17, 18, 31, 32, 33, 64, 100, 125, 200, 256):
+        cases.append(rng.integers(0, 6, n).astype(np.float32))            # many exact ties
+        cases.append(rng.integers(0, max(2, n // 2), n).astype(np.float32))
+        cases.append(rng.uniform(size=n).astype(np.float32))
+        cases.append(np.arange(n, dtype=np.float32))
+        cases.append(np.arange(n, dtype=np.float32)[::-1].copy())
+        cases.append(np.concatenate([np.arange(n // 2), np.arange(n - n // 2)[::-1]]).astype(np.float32))
+        if n > 16:
+            cases.append(ref.std_sort_killer(n))
+            cases.append(ref.std_sort_killer(n, ties=2))               # the adversary's shape with pairs of exact ties
+            cases.append(ref.std_sort_killer(n, ties=3))
+    h0 = oracle.L.gpo_sort_replay_heapsorts()
+    for k in cases:
+        a = ref.std_sort_indices(k)
+        b = oracle.sort_replay(k)
+        assert np.array_equal(a, b), (len(k), k[:20])
+        assert np.all(np.diff(k[a]) >= 0)
+    # the adversarial inputs really tripped the depth limit, with ties present (so the fallback's move order matters)
+    assert oracle.L.gpo_sort_replay_heapsorts() - h0 >= 10
