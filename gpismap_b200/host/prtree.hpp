@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <unordered_map>
 #include <vector>
 
 namespace gpismap_host {
@@ -73,12 +74,25 @@ public:
     }
 
     // ---- IsNotNew (octree.cpp:431-458)
-    bool is_not_new(const float* p) const { return is_not_new(root_, p); }
+    bool is_not_new(const float* p) const {
+        const int c = find_cluster(p);
+        if (c >= 0) return is_not_new(c, p);      // same recursion, entered at the leaf's cluster-level cell
+        if (c == kAbsent) return false;            // no cluster-level cell there: the descent ends in an empty leaf
+        return is_not_new(root_, p);
+    }
 
     // ---- Insert(n, quads) from the root (octree.cpp:295-414 / quadtree.cpp:223-312); follows root
     // growth (t = t->getRoot(), GPisMap3.cpp:615-618). `touched` receives the cluster-level cells the
     // insertion registered (vecInserted).
     bool insert(int s, std::vector<int>& touched) {
+        const int c = find_cluster(samples_[s].pos);
+        if (c >= 0) {
+            // enter the recursion at the cluster-level cell; the ancestors would only have passed the call down
+            // (their own boxes contain the point, one child can take it) and refreshed their counts on the way back
+            const bool ok = insert_rec(c, s, &touched);
+            if (ok) for (int a = cells_[c].parent; a >= 0; a = cells_[a].parent) update_count(a);
+            return ok;
+        }
         const bool ok = insert_rec(root_, s, &touched);
         while (cells_[root_].parent >= 0) root_ = cells_[root_].parent;
         return ok;
@@ -86,9 +100,9 @@ public:
 
     // ---- Remove(n, set) (octree.cpp:510-566); cells deleted by a collapse are reported in `freed`
     // (the reference erases them from the active set).
-    bool remove_tracked(int s, std::vector<int>& freed) { return remove_rec(root_, samples_[s].pos, true, &freed); }
+    bool remove_tracked(int s, std::vector<int>& freed) { return remove_from(samples_[s].pos, true, &freed); }
     // ---- Remove(n) (octree.cpp:460-508): visits every child, collapses, reports freed cells too
-    bool remove_plain(int s, std::vector<int>& freed) { return remove_rec(root_, samples_[s].pos, false, &freed); }
+    bool remove_plain(int s, std::vector<int>& freed) { return remove_from(samples_[s].pos, false, &freed); }
 
     // ---- QueryRange (octree.cpp:777-804): samples with |p - c|^2 < (half)^2, DFS order
     void query_range(const float* c, float half, std::vector<int>& out) const {
@@ -211,6 +225,7 @@ private:
             const uint32_t g = ch.gen;
             init_cell(ch, c, l, id, true);
             ch.gen = g;
+            index_add(b + k);
         }
         cells_[id].child0 = b;
         (void)except_k; (void)except_cell;
@@ -221,6 +236,76 @@ private:
         int s = 0;
         for (int k = 0; k < NCH; ++k) s += cells_[n.child0 + k].count;
         n.count = s;
+    }
+    // ---- direct entry at the cluster level. Every descent from the root passes 7+ levels whose only effect, for a
+    // point that is not within a few ulps of a lattice plane, is to hand the call to the one child that contains it.
+    // The index maps a cluster-level lattice cell to its tree cell; points near a plane (or trees with an orphaned
+    // subtree) take the full descent, so the visited nodes and every float comparison that can matter are the same.
+    static constexpr int kUnsafe = -1, kAbsent = -2;
+    std::unordered_map<uint64_t, int32_t> cluster_index_;
+    static uint64_t lattice_key(const long long* i) {
+        uint64_t k = 0;
+        for (int a = 0; a < D; ++a) k = k * 0x9E3779B97F4A7C15ull + (uint64_t)(i[a] + (1ll << 40));
+        return k;
+    }
+    uint64_t key_of_cell(int id) const {
+        long long i[D];
+        const double pitch = 2.0 * (double)P.cluster_half;
+        for (int a = 0; a < D; ++a) i[a] = (long long)std::floor((double)cells_[id].c[a] / pitch);
+        return lattice_key(i);
+    }
+    void index_add(int id) { if (is_cluster_level(id)) cluster_index_[key_of_cell(id)] = id; }
+    void index_del(int id) {
+        if (!is_cluster_level(id)) return;
+        auto it = cluster_index_.find(key_of_cell(id));
+        if (it != cluster_index_.end() && it->second == id) cluster_index_.erase(it);
+    }
+    int find_cluster(const float* p) const {
+        if (orphaned_ || !contains(cells_[root_], p)) return kUnsafe;
+        const double pitch = 2.0 * (double)P.cluster_half;
+        const float rh = cells_[root_].half;
+        long long i[D];
+        for (int a = 0; a < D; ++a) {
+            const double q = (double)p[a] / pitch;
+            const double f = std::floor(q);
+            // distance to the nearest lattice plane, against the largest tolerance any level of the descent would use
+            // (certain_child: 8 ulp of |c| + half, here with the root's half and the root centre's magnitude)
+            const double tol = 4.0 * 9.6e-7 * ((double)std::fabs(p[a]) + (double)std::fabs(cells_[root_].c[a]) + 2.0 * (double)rh);
+            const double dist = std::min(q - f, f + 1.0 - q) * pitch;
+            if (!(dist > tol)) return kUnsafe;
+            i[a] = (long long)f;
+        }
+        auto it = cluster_index_.find(lattice_key(i));
+        return it == cluster_index_.end() ? kAbsent : it->second;
+    }
+    // Remove entered at the cluster-level cell, then the ancestors' part of remove_rec (collapse when all children are
+    // empty leaves, refresh the count) walked upwards
+    bool remove_from(const float* p, bool short_circuit, std::vector<int>* freed) {
+        const int c = find_cluster(p);
+        if (c == kAbsent) return false;
+        if (c < 0) return remove_rec(root_, p, short_circuit, freed);
+        const bool res = remove_rec(c, p, short_circuit, freed);
+        for (int a = cells_[c].parent; a >= 0; a = cells_[a].parent) remove_finish(a, res, freed);
+        return res;
+    }
+    void remove_finish(int id, bool res, std::vector<int>* freed) {
+        if (res && cells_[id].child0 >= 0) {
+            bool all_empty = true;
+            for (int k = 0; k < NCH; ++k) all_empty = all_empty && is_empty_leaf(cells_[id].child0 + k);
+            if (all_empty) {
+                const int b = cells_[id].child0;
+                for (int k = 0; k < NCH; ++k) {
+                    if (freed) freed->push_back(b + k);
+                    index_del(b + k);
+                    cells_[b + k].alive = false;
+                    cells_[b + k].gen++;
+                }
+                free_blocks_.push_back(b);
+                cells_[id].child0 = -1;
+                cells_[id].count = 0;
+            }
+        }
+        update_count(id);
     }
     void log_mutation(int id) {
         if (!mutation_log) return;
@@ -269,6 +354,7 @@ private:
                 const uint32_t g = ch.gen;
                 init_cell(ch, c, hl, par, true);
                 ch.gen = g;
+                index_add(b + k);
             }
             move_cell(id, b + child_k);
             cells_[b + child_k].parent = par;
@@ -287,6 +373,8 @@ private:
         cells_[to].gen = g;
         if (cells_[to].child0 >= 0)
             for (int k = 0; k < NCH; ++k) cells_[cells_[to].child0 + k].parent = to;
+        index_del(from);
+        index_add(to);
         cells_[from].alive = false;
         cells_[from].gen++;
         cells_[from].child0 = -1; cells_[from].sample = -1;
@@ -373,22 +461,7 @@ private:
             if (short_circuit && res) break;
             res = remove_rec(cells_[id].child0 + k, p, short_circuit, freed) || res;
         }
-        if (res) {
-            bool all_empty = true;
-            for (int k = 0; k < NCH; ++k) all_empty = all_empty && is_empty_leaf(cells_[id].child0 + k);
-            if (all_empty) {
-                const int b = cells_[id].child0;
-                for (int k = 0; k < NCH; ++k) {
-                    if (freed) freed->push_back(b + k);
-                    cells_[b + k].alive = false;
-                    cells_[b + k].gen++;
-                }
-                free_blocks_.push_back(b);
-                cells_[id].child0 = -1;
-                cells_[id].count = 0;
-            }
-        }
-        update_count(id);
+        remove_finish(id, res, freed);
         return res;
     }
 
