@@ -98,6 +98,7 @@ struct GPisMap3::Impl {
     struct ReOut { int action; float pos_new[3], grad_new[3], noise, grad_noise; };   // 0 nothing, 1 double the sigmas, 2 replace
     ReOut reeval_compute(const ReEval& e, const float* rinv0, const float* var) const;
     void reeval_commit(const ReEval& e, const ReOut& o);
+    std::vector<int> scratch_freed, scratch_touched;   // reeval_commit runs once per in-view sample
     void reeval_apply(const ReEval& e, const float* rinv0, const float* var);
 };
 
@@ -421,11 +422,12 @@ void GPisMap3::Impl::reeval_commit(const ReEval& e, const ReOut& o) {
     const float* pos_new = o.pos_new;
     const float* grad_new = o.grad_new;
     // remove the old sample (GPisMap3.cpp:536), then try the fused one
-    std::vector<int> freed;
+    std::vector<int>& freed = scratch_freed;
+    freed.clear();
     tree->remove_tracked(e.sample, freed);
     core.drop_freed(freed);
     if ((double)noise > 1.0 && (double)grad_noise > 0.61) return;
-    std::vector<int> touched;
+    std::vector<int>& touched = scratch_touched;
     const int s = core.try_insert(pos_new, touched);
     if (s < 0) return;
     Sample<3>& sm = tree->sample(s);

@@ -41,6 +41,42 @@ struct LeafHandle {
     bool operator<(const LeafHandle& o) const { return cell < o.cell || (cell == o.cell && gen < o.gen); }
 };
 
+// activeSet (GPisMap3.h:91, std::unordered_set<OcTree*> in the reference): a list plus a per-cell mark instead of a
+// node-based set — every accepted sample activates its leaf, so insert() runs ~10^5 times per frame. A handle is
+// live while mark[cell] == gen + 1; handles of freed cells are dropped by erase() or fail cell_alive() later.
+class ActiveSet {
+public:
+    void insert(const LeafHandle& h) {
+        if ((size_t)h.cell >= mark_.size()) mark_.resize((size_t)h.cell + 1 + mark_.size() / 2, 0);
+        if (mark_[h.cell] == h.gen + 1) return;
+        if (mark_[h.cell] == 0) ++live_;
+        mark_[h.cell] = h.gen + 1;
+        items_.push_back(h);
+    }
+    void erase(const LeafHandle& h) {
+        if ((size_t)h.cell < mark_.size() && mark_[h.cell] == h.gen + 1) { mark_[h.cell] = 0; --live_; }
+    }
+    void clear() {
+        for (const LeafHandle& h : items_) mark_[h.cell] = 0;
+        items_.clear();
+        live_ = 0;
+    }
+    size_t size() const { return live_; }
+    // live handles in (cell, generation) order — the iteration order of the std::set this replaces
+    std::vector<LeafHandle> sorted() const {
+        std::vector<LeafHandle> v;
+        v.reserve(live_);
+        for (const LeafHandle& h : items_) if (mark_[h.cell] == h.gen + 1) v.push_back(h);
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end(), [](const LeafHandle& a, const LeafHandle& b) { return a.cell == b.cell && a.gen == b.gen; }), v.end());
+        return v;
+    }
+private:
+    std::vector<LeafHandle> items_;
+    std::vector<uint32_t> mark_;
+    size_t live_ = 0;
+};
+
 template <int D>
 class MapCore {
 public:
@@ -53,7 +89,7 @@ public:
     int device_;
     Tree* tree = nullptr;
     gpis_ctx* ctx = nullptr;
-    std::set<LeafHandle> active;                      // activeSet (GPisMap3.h:91)
+    ActiveSet active;                                 // activeSet (GPisMap3.h:91)
     std::map<uint64_t, std::array<int32_t, 3>> device_cells;   // leaves currently registered on the device
     std::map<uint64_t, std::array<float, 6>> device_boxes;     // effective boxes sent for them (only non-default ones)
     int last_trained = 0;
@@ -103,14 +139,15 @@ public:
     // at least one leaf; -1 otherwise (the sample may still sit in the tree).
     int try_insert(const float* pos, std::vector<int>& touched, const float* full = nullptr) {
         touched.clear();
-        if (tree->is_not_new(pos)) return -1;
+        const int at = tree->locate(pos);              // one look-up of the cluster-level cell for both steps
+        if (tree->is_not_new_at(at, pos)) return -1;
         const int s = tree->new_sample(pos);
         if (full) {   // bulk load: the sample carries its data from the start, like ref_harness.cpp does
             Sample<D>& sm = tree->sample(s);
             for (int a = 0; a < D; ++a) sm.grad[a] = full[D + a];
             sm.val = full[2 * D]; sm.pose_sig = full[2 * D + 1]; sm.grad_sig = full[2 * D + 2];
         }
-        const bool ok = tree->insert(s, touched);
+        const bool ok = tree->insert_at(at, s, touched);
         if (!ok || touched.empty()) return -1;
         return s;
     }
@@ -176,7 +213,7 @@ public:
         g_prof_s[6] += now_s() - tp0; g_prof_n[6] += 1;
         std::vector<int32_t> acells;
         float radius = rtimes_ * tparam.cluster_half;
-        for (const LeafHandle& h : active) {
+        for (const LeafHandle& h : active.sorted()) {
             if (!tree->cell_alive(h.cell, h.gen) || tree->is_empty_leaf(h.cell)) continue;
             int32_t cc[3];
             cell_of(h.cell, cc);
@@ -210,7 +247,7 @@ public:
         std::set<int> update_set;
         std::vector<int> qs;
         double tp0 = now_s();
-        for (const LeafHandle& h : active) {
+        for (const LeafHandle& h : active.sorted()) {
             if (!tree->cell_alive(h.cell, h.gen)) continue;
             update_set.insert(h.cell);
             const auto& n = tree->cell(h.cell);
@@ -388,7 +425,7 @@ public:
         tree->query_clusters(zero, 1.0e6f, all);
         for (int cid : all) {
             for (int a = 0; a < D; ++a) centres.push_back(tree->cell(cid).c[a]);
-            counts.push_back(tree->cell(cid).count);
+            counts.push_back(tree->count(cid));
         }
     }
     // bulk load, mirroring oracle/ref_harness.cpp ref3_insert_samples

@@ -39,6 +39,7 @@ template <int D>
 class PRTree {
 public:
     static constexpr int NCH = 1 << D;
+    static constexpr int kUnsafe = -1, kAbsent = -2;   // find_cluster: take the full descent / no cluster-level cell there
     struct Cell {
         float c[D];
         float half;
@@ -46,7 +47,6 @@ public:
         int32_t parent = -1;
         int32_t child0 = -1;     // first of NCH consecutive children, -1 = leaf
         int32_t sample = -1;
-        int32_t count = 0;       // numNodes
         uint32_t gen = 0;        // bumped when the cell is freed (stale-handle detection)
         bool max_depth = false, root_limit = false, alive = true;
     };
@@ -59,6 +59,7 @@ public:
 
     int root() const { return root_; }
     const Cell& cell(int i) const { return cells_[i]; }
+    int32_t count(int i) const { return count_[i]; }       // numNodes
     const Sample<D>& sample(int s) const { return samples_[s]; }
     Sample<D>& sample(int s) { return samples_[s]; }
     bool cell_alive(int i, uint32_t gen) const { return i >= 0 && i < (int)cells_.size() && cells_[i].alive && cells_[i].gen == gen; }
@@ -74,8 +75,11 @@ public:
     }
 
     // ---- IsNotNew (octree.cpp:431-458)
-    bool is_not_new(const float* p) const {
-        const int c = find_cluster(p);
+    // locate(p) = the cluster-level cell to enter at (or kUnsafe / kAbsent); valid until the next structural change
+    // above the cluster level, i.e. it may be shared by an is_not_new_at / insert_at pair on the same point
+    int locate(const float* p) const { return find_cluster(p); }
+    bool is_not_new(const float* p) const { return is_not_new_at(find_cluster(p), p); }
+    bool is_not_new_at(int c, const float* p) const {
         if (c >= 0) return is_not_new(c, p);      // same recursion, entered at the leaf's cluster-level cell
         if (c == kAbsent) return false;            // no cluster-level cell there: the descent ends in an empty leaf
         return is_not_new(root_, p);
@@ -84,8 +88,8 @@ public:
     // ---- Insert(n, quads) from the root (octree.cpp:295-414 / quadtree.cpp:223-312); follows root
     // growth (t = t->getRoot(), GPisMap3.cpp:615-618). `touched` receives the cluster-level cells the
     // insertion registered (vecInserted).
-    bool insert(int s, std::vector<int>& touched) {
-        const int c = find_cluster(samples_[s].pos);
+    bool insert(int s, std::vector<int>& touched) { return insert_at(find_cluster(samples_[s].pos), s, touched); }
+    bool insert_at(int c, int s, std::vector<int>& touched) {
         if (c >= 0) {
             // enter the recursion at the cluster-level cell; the ancestors would only have passed the call down
             // (their own boxes contain the point, one child can take it) and refreshed their counts on the way back
@@ -158,6 +162,8 @@ public:
 private:
     TreeParam P;
     std::vector<Cell> cells_;
+    std::vector<int32_t> count_;         // numNodes per cell, kept apart from the 60-byte cells: the ancestor walks of
+                                         // every insert / remove read the eight children's counts (one 32-byte run)
     std::vector<Sample<D>> samples_;
     std::vector<int32_t> free_blocks_;   // recycled child blocks
     int root_ = -1;
@@ -174,12 +180,13 @@ private:
     }
     void init_cell(Cell& n, const float* c, float half, int parent, bool derive_flags) {
         for (int a = 0; a < D; ++a) { n.c[a] = c[a]; n.lo[a] = c[a] - half; n.hi[a] = c[a] + half; }
-        n.half = half; n.parent = parent; n.child0 = -1; n.sample = -1; n.count = 0; n.alive = true;
+        n.half = half; n.parent = parent; n.child0 = -1; n.sample = -1; n.alive = true;
         n.max_depth = derive_flags && (half < P.min_half);     // octree.cpp:72-75
         n.root_limit = derive_flags && (half > P.max_half);
     }
     int new_cell(const float* c, float half, int parent, bool derive_flags) {
         cells_.emplace_back();
+        count_.push_back(0);
         init_cell(cells_.back(), c, half, parent, derive_flags);
         return (int)cells_.size() - 1;
     }
@@ -187,6 +194,7 @@ private:
         if (!free_blocks_.empty()) { const int b = free_blocks_.back(); free_blocks_.pop_back(); return b; }
         const int b = (int)cells_.size();
         cells_.resize(cells_.size() + NCH);
+        count_.resize(cells_.size(), 0);
         return b;
     }
     bool contains(const Cell& n, const float* p) const {    // strict, octree.h:119-126
@@ -225,24 +233,71 @@ private:
             const uint32_t g = ch.gen;
             init_cell(ch, c, l, id, true);
             ch.gen = g;
+            count_[b + k] = 0;
             index_add(b + k);
         }
         cells_[id].child0 = b;
         (void)except_k; (void)except_cell;
     }
     void update_count(int id) {
-        Cell& n = cells_[id];
-        if (n.child0 < 0) return;
+        const int b = cells_[id].child0;
+        if (b < 0) return;
         int s = 0;
-        for (int k = 0; k < NCH; ++k) s += cells_[n.child0 + k].count;
-        n.count = s;
+        for (int k = 0; k < NCH; ++k) s += count_[b + k];
+        count_[id] = s;
     }
     // ---- direct entry at the cluster level. Every descent from the root passes 7+ levels whose only effect, for a
     // point that is not within a few ulps of a lattice plane, is to hand the call to the one child that contains it.
     // The index maps a cluster-level lattice cell to its tree cell; points near a plane (or trees with an orphaned
     // subtree) take the full descent, so the visited nodes and every float comparison that can matter are the same.
-    static constexpr int kUnsafe = -1, kAbsent = -2;
-    std::unordered_map<uint64_t, int32_t> cluster_index_;
+    // open addressing, linear probing; value 0 = empty slot, -1 = tombstone, otherwise cell id + 1
+    struct ClusterIndex {
+        std::vector<uint64_t> keys;
+        std::vector<int32_t> vals;
+        size_t used = 0, live = 0;
+        ClusterIndex() : keys(1024, 0), vals(1024, 0) {}
+        static size_t mix(uint64_t k) { k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull; k ^= k >> 32; return (size_t)k; }
+        int32_t find(uint64_t k) const {
+            const size_t m = keys.size() - 1;
+            for (size_t i = mix(k) & m;; i = (i + 1) & m) {
+                if (vals[i] == 0) return -1;
+                if (vals[i] > 0 && keys[i] == k) return vals[i] - 1;
+            }
+        }
+        void set(uint64_t k, int32_t id) {
+            if ((used + 1) * 2 > keys.size()) rehash();
+            const size_t m = keys.size() - 1;
+            size_t tomb = (size_t)-1;
+            for (size_t i = mix(k) & m;; i = (i + 1) & m) {
+                if (vals[i] == 0) {
+                    if (tomb != (size_t)-1) i = tomb; else ++used;
+                    keys[i] = k; vals[i] = id + 1; ++live;
+                    return;
+                }
+                if (vals[i] < 0) { if (tomb == (size_t)-1) tomb = i; }
+                else if (keys[i] == k) { vals[i] = id + 1; return; }
+            }
+        }
+        void erase_if(uint64_t k, int32_t id) {
+            const size_t m = keys.size() - 1;
+            for (size_t i = mix(k) & m;; i = (i + 1) & m) {
+                if (vals[i] == 0) return;
+                if (vals[i] > 0 && keys[i] == k) { if (vals[i] - 1 == id) { vals[i] = -1; --live; } return; }
+            }
+        }
+        void rehash() {
+            std::vector<uint64_t> ok; std::vector<int32_t> ov;
+            ok.swap(keys); ov.swap(vals);
+            const size_t cap = std::max<size_t>(1024, live * 4 <= ok.size() ? ok.size() : ok.size() * 2);
+            keys.assign(cap, 0); vals.assign(cap, 0);
+            used = 0; live = 0;
+            for (size_t i = 0; i < ok.size(); ++i) if (ov[i] > 0) set(ok[i], ov[i] - 1);
+        }
+    };
+    ClusterIndex cluster_index_;
+    // the previous look-up: consecutive pixels of a depth image mostly fall into the same leaf
+    mutable uint64_t last_key_ = 0;
+    mutable int32_t last_id_ = kUnsafe;   // kUnsafe = nothing cached
     static uint64_t lattice_key(const long long* i) {
         uint64_t k = 0;
         for (int a = 0; a < D; ++a) k = k * 0x9E3779B97F4A7C15ull + (uint64_t)(i[a] + (1ll << 40));
@@ -254,11 +309,11 @@ private:
         for (int a = 0; a < D; ++a) i[a] = (long long)std::floor((double)cells_[id].c[a] / pitch);
         return lattice_key(i);
     }
-    void index_add(int id) { if (is_cluster_level(id)) cluster_index_[key_of_cell(id)] = id; }
+    void index_add(int id) { if (is_cluster_level(id)) { cluster_index_.set(key_of_cell(id), id); last_id_ = kUnsafe; } }
     void index_del(int id) {
         if (!is_cluster_level(id)) return;
-        auto it = cluster_index_.find(key_of_cell(id));
-        if (it != cluster_index_.end() && it->second == id) cluster_index_.erase(it);
+        cluster_index_.erase_if(key_of_cell(id), id);
+        last_id_ = kUnsafe;
     }
     int find_cluster(const float* p) const {
         if (orphaned_ || !contains(cells_[root_], p)) return kUnsafe;
@@ -275,8 +330,12 @@ private:
             if (!(dist > tol)) return kUnsafe;
             i[a] = (long long)f;
         }
-        auto it = cluster_index_.find(lattice_key(i));
-        return it == cluster_index_.end() ? kAbsent : it->second;
+        const uint64_t key = lattice_key(i);
+        if (last_id_ != kUnsafe && last_key_ == key) return last_id_;
+        const int32_t id = cluster_index_.find(key);
+        last_key_ = key;
+        last_id_ = id < 0 ? kAbsent : id;
+        return last_id_;
     }
     // Remove entered at the cluster-level cell, then the ancestors' part of remove_rec (collapse when all children are
     // empty leaves, refresh the count) walked upwards
@@ -290,8 +349,11 @@ private:
     }
     void remove_finish(int id, bool res, std::vector<int>* freed) {
         if (res && cells_[id].child0 >= 0) {
+            // a live empty leaf always carries count 0 (every site that clears `sample` of a leaf clears the count),
+            // so the eight-cell scan can only succeed when the children's counts sum to 0
             bool all_empty = true;
-            for (int k = 0; k < NCH; ++k) all_empty = all_empty && is_empty_leaf(cells_[id].child0 + k);
+            for (int k = 0; k < NCH; ++k) all_empty = all_empty && count_[cells_[id].child0 + k] == 0;
+            for (int k = 0; all_empty && k < NCH; ++k) all_empty = is_empty_leaf(cells_[id].child0 + k);
             if (all_empty) {
                 const int b = cells_[id].child0;
                 for (int k = 0; k < NCH; ++k) {
@@ -302,7 +364,7 @@ private:
                 }
                 free_blocks_.push_back(b);
                 cells_[id].child0 = -1;
-                cells_[id].count = 0;
+                count_[id] = 0;
             }
         }
         update_count(id);
@@ -354,6 +416,7 @@ private:
                 const uint32_t g = ch.gen;
                 init_cell(ch, c, hl, par, true);
                 ch.gen = g;
+                count_[b + k] = 0;
                 index_add(b + k);
             }
             move_cell(id, b + child_k);
@@ -371,6 +434,7 @@ private:
         const uint32_t g = cells_[to].gen;
         cells_[to] = cells_[from];
         cells_[to].gen = g;
+        count_[to] = count_[from];
         if (cells_[to].child0 >= 0)
             for (int k = 0; k < NCH; ++k) cells_[cells_[to].child0 + k].parent = to;
         index_del(from);
@@ -392,7 +456,7 @@ private:
         }
         if (cells_[id].max_depth) {
             if (cells_[id].sample < 0) {
-                cells_[id].sample = s; cells_[id].count = 1;
+                cells_[id].sample = s; count_[id] = 1;
                 log_mutation(id);
                 if (quads && P.reg_at_maxdepth && reg_ok(cells_[id])) quads->push_back(id);
                 return true;
@@ -404,7 +468,7 @@ private:
                 subdivide(id);
             } else {
                 if (cells_[id].sample < 0) {
-                    cells_[id].sample = s; cells_[id].count = 1;
+                    cells_[id].sample = s; count_[id] = 1;
                     log_mutation(id);
                     if (quads && reg_ok(cells_[id])) quads->push_back(id);
                     return true;
@@ -450,7 +514,7 @@ private:
         if (!contains(cells_[id], p)) return false;
         if (is_empty_leaf(id)) return false;
         if (cells_[id].sample >= 0 && (double)sqdist(samples_[cells_[id].sample].pos, p) < 1e-12) {   // EPS, octree.cpp:22
-            cells_[id].sample = -1; cells_[id].count = 0;
+            cells_[id].sample = -1; count_[id] = 0;
             log_mutation(id);
             return true;
         }

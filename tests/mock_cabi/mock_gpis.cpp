@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "gpis_b200.h"
@@ -154,6 +155,7 @@ int gpis_leaves_train_dirty(gpis_ctx* c, int n_active, const int32_t* active, fl
             }
         const int N = (int)(ball.size() / w);
         if (N <= 0) continue;
+        if (std::getenv("GPIS_MOCK_SKIP_TRAIN")) { c->st.last_train_leaves++; continue; }   // host-profile runs: the samples do not depend on the leaf GPs
         gpo_gp_free(D->gp);
         D->gp = gpo_gp_train(dim, ball.data(), N, c->cfg.map_scale, c->cfg.map_noise);
         D->N = N;
