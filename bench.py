@@ -241,6 +241,10 @@ def main():
             st_r = ctx.stats()
             repl_ms.append(st_r["last_replicate_ms"])
             repl_mb.append(st_r["last_replicate_bytes"] / 1e6)
+    # leaf training overlaps the next frame's host work (gpis_set_train_mode): the last batch is still in flight here
+    t0 = time.perf_counter()
+    ctx.train_wait()
+    final_wait_ms = 1e3 * (time.perf_counter() - t0)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
@@ -385,6 +389,8 @@ def main():
                     "arena_gb": sq["arena_bytes_used"] / 1e9, "build_s": t_build,
                     "update_ms_per_frame_median": float(np.median(update_ms)) if update_ms else None,
                     "update_ms_per_frame_p90": float(np.percentile(update_ms, 90)) if update_ms else None,
+                    "update_ms_per_frame_mean_incl_final_train_wait": float((np.sum(update_ms) + final_wait_ms) / len(update_ms)) if update_ms else None,
+                    "train_mode": int(os.environ.get("GPIS_TRAIN_MODE", "2")),
                     "train_kernel_ms_per_frame_median": float(np.median(train_ms)) if train_ms else None},
         }
         if world == 1 and not args.no_cpu_baseline:

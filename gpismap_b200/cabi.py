@@ -21,6 +21,7 @@ EXPORTS = [
     "gpis_obs_train_2d", "gpis_obs_train_1d", "gpis_obs_test",
     "gpis_get_stats", "gpis_comm_unique_id", "gpis_comm_init", "gpis_replicate",
     "gpis_snapshot_save", "gpis_snapshot_load", "gpis_samples_set", "gpis_leaves_train_dirty", "gpis_frame_eval", "gpis_reeval",
+    "gpis_set_train_mode", "gpis_train_wait",
 ]
 
 
@@ -89,6 +90,8 @@ def lib():
         L.gpis_replicate.argtypes = [vp, C.c_int]
         L.gpis_snapshot_save.argtypes = [vp, C.c_char_p]
         L.gpis_snapshot_load.argtypes = [vp, C.c_char_p]
+        L.gpis_set_train_mode.argtypes = [vp, C.c_int]
+        L.gpis_train_wait.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -228,6 +231,12 @@ class Ctx:
         var = np.zeros(m, np.float32) if var is None else np.ascontiguousarray(var, np.float32).copy()
         self._ck(lib().gpis_obs_test(self.h, _p(xt), d, m, _p(val), _p(var)))
         return val, var
+
+    def set_train_mode(self, mode):
+        self._ck(lib().gpis_set_train_mode(self.h, mode))
+
+    def train_wait(self):
+        self._ck(lib().gpis_train_wait(self.h))
 
     def stats(self):
         s = Stats()

@@ -141,11 +141,31 @@ struct HostLeaf {
 
 struct ArenaChunk { unsigned char* base; uint64_t size; };
 
+// One training batch between "records reserved, samples gathered, jobs uploaded" and "records installed in the table".
+// With gpis_set_train_mode(ctx, 1 | 2) the batch stays in this state after gpis_leaves_train_dirty returns: K1 runs on
+// its own stream while the host works on the next frame, and every entry point that reads or changes records, the
+// table or the arena completes it first (train_flush).
+struct TrainPlan { uint64_t key; int N, ng, n, nb; uint64_t rec, rb; };
+struct PendingTrain {
+    bool active = false, launched = false;
+    std::vector<TrainPlan> plan;
+    int njobs = 0, maxN = 1, maxnb = 1;
+};
+
 struct gpis_ctx {
     gpis_config cfg;
     std::string err;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // asynchronous leaf training (gpis_set_train_mode)
+    cudaStream_t train_stream = nullptr;
+    cudaEvent_t ev_train[3] = {nullptr, nullptr, nullptr};   // inputs ready (main stream) | K1 start | K1 done (training stream)
+    int train_mode = 0;                                      // 0 synchronous, 1 launch at once, 2 launch at the next gpis_reeval
+    PendingTrain pend;
+    void* d_train_smp = nullptr; uint64_t train_smp_bytes = 0;     // gathered training balls (CSR) of the pending batch
+    void* d_train_jobs = nullptr; uint64_t train_jobs_bytes = 0;   // its jobs + status
+    int* d_k1_counter = nullptr;                                   // job counter of the persistent K1 CTAs
+    bool train_ms_pending = false;                                 // ev_train[1..2] recorded, elapsed time not read yet
     // leaf table
     LeafTable T{};
     uint32_t table_cap = 0;
@@ -216,6 +236,12 @@ struct NvtxRange {
             return GPIS_ERR_CUDA;                                                                  \
         }                                                                                          \
     } while (0)
+
+extern "C" {
+static int train_launch(gpis_ctx* ctx);   // start the pending batch's K1 (no wait)
+static int train_flush(gpis_ctx* ctx);    // ... and wait for it, install its records
+static void train_discard(gpis_ctx* ctx); // wait and drop it (reset / destroy)
+}
 
 static int ensure(gpis_ctx* ctx, void** p, uint64_t* cap, uint64_t need) {
     if (*cap >= need) return 0;
@@ -418,6 +444,13 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
     CK(cudaSetDevice(cfg->device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ctx->ev[i]));
+    {   // the training stream yields to the main stream: a frame's small kernels should not queue behind K1's CTAs
+        int lo_prio = 0, hi_prio = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CK(cudaStreamCreateWithPriority(&ctx->train_stream, cudaStreamNonBlocking, lo_prio));
+        for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&ctx->ev_train[i]));
+        CK(cudaMalloc(&ctx->d_k1_counter, 256));
+    }
     derive_params(ctx);
     uint32_t cap = 4096;
     while (cap < (uint32_t)std::max(1, cfg->max_leaves) * 2u) cap *= 2;
@@ -436,6 +469,7 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
 void gpis_destroy(gpis_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
+    train_discard(ctx);
     cudaDeviceSynchronize();
     for (auto& c : ctx->chunks) cudaFree(c.base);
     cudaFree(ctx->T.keys); cudaFree(ctx->T.vals); cudaFree(ctx->T.centre); cudaFree(ctx->T.cell);
@@ -447,6 +481,9 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->obs_tiles); cudaFree(ctx->obs_desc); cudaFree(ctx->obs_b0); cudaFree(ctx->obs_b1);
     cudaFree(ctx->d_acc); cudaFree(ctx->store.ptr); cudaFree(ctx->store.cnt); cudaFree(ctx->d_gather); cudaFree(ctx->d_frame); cudaFree(ctx->d_reeval);
     cudaFree(ctx->d_repl); cudaFree(ctx->d_repl_idx); cudaFree(ctx->d_repl_jobs);
+    cudaFree(ctx->d_train_smp); cudaFree(ctx->d_train_jobs); cudaFree(ctx->d_k1_counter);
+    for (int i = 0; i < 3; ++i) if (ctx->ev_train[i]) cudaEventDestroy(ctx->ev_train[i]);
+    if (ctx->train_stream) cudaStreamDestroy(ctx->train_stream);
     if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -459,6 +496,7 @@ int gpis_device(const gpis_ctx* ctx) { return ctx ? ctx->cfg.device : -1; }
 int gpis_reset(gpis_ctx* ctx) {
     if (!ctx) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    train_discard(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->leaves.clear();
     ctx->free_slots.clear();
@@ -558,6 +596,7 @@ static int take_slot(gpis_ctx* ctx, uint64_t key) {
 int gpis_leaves_mark(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres) {
     if (!ctx || n_leaves < 0 || (n_leaves > 0 && (!cells || !centres))) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     const int dim = ctx->cfg.dim;
     int rc = table_reserve(ctx, n_leaves);
     if (rc) return rc;
@@ -578,6 +617,7 @@ int gpis_leaves_mark(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const fl
 int gpis_leaves_set_boxes(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* boxes) {
     if (!ctx || n_leaves < 0 || (n_leaves > 0 && (!cells || !boxes))) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     const int dim = ctx->cfg.dim;
     std::vector<SlotUpdate> ups;
     for (int i = 0; i < n_leaves; ++i) {
@@ -596,6 +636,7 @@ int gpis_leaves_set_boxes(gpis_ctx* ctx, int n_leaves, const int32_t* cells, con
 int gpis_leaves_erase(gpis_ctx* ctx, int n_leaves, const int32_t* cells) {
     if (!ctx || n_leaves < 0 || (n_leaves > 0 && !cells)) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     const int dim = ctx->cfg.dim;
     std::vector<SlotUpdate> ups;
     std::vector<StoreUpdate> store_clear;
@@ -643,7 +684,7 @@ static int train_jobs(gpis_ctx* ctx, std::vector<TrainJob>& jobs, const float* d
     int32_t* d_st = (int32_t*)((unsigned char*)ctx->d_jobs + b_jobs);
     CK(cudaMemcpyAsync(d_jobs, sorted.data(), sorted.size() * sizeof(TrainJob), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = launch_leaf_train(ctx->stream, d_jobs, (int)sorted.size(), d_smp, ctx->tp, d_st, maxN, maxnb, ctx->err);
+    rc = launch_leaf_train(ctx->stream, d_jobs, (int)sorted.size(), d_smp, ctx->tp, d_st, maxN, maxnb, 2 * ctx->num_sms, ctx->d_k1_counter, ctx->err);
     if (rc) return rc;
     ctx->st.kernel_launches++;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -656,6 +697,90 @@ static int train_jobs(gpis_ctx* ctx, std::vector<TrainJob>& jobs, const float* d
     return 0;
 }
 
+// ---- asynchronous training (gpis_set_train_mode). The batch's device-side inputs (gathered balls in d_train_smp, jobs
+// in d_train_jobs) were written on the main stream; K1 runs on the training stream behind an event.
+static int train_launch(gpis_ctx* ctx) {
+    PendingTrain& pd = ctx->pend;
+    if (!pd.active || pd.launched) return 0;
+    NvtxRange nvtx_("K1 leaf train (launch)");
+    const uint64_t b_jobs = align_up((uint64_t)pd.njobs * sizeof(TrainJob), 256);
+    TrainJob* d_jobs = (TrainJob*)ctx->d_train_jobs;
+    int32_t* d_st = (int32_t*)((unsigned char*)ctx->d_train_jobs + b_jobs);
+    CK(cudaEventRecord(ctx->ev_train[0], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->train_stream, ctx->ev_train[0], 0));
+    CK(cudaEventRecord(ctx->ev_train[1], ctx->train_stream));
+    // overlapped launches keep a few CTA slots free: the on-demand observation tests of the frame in progress (a handful
+    // of points each) must not wait for a leaf to finish
+    static const int reserve = std::getenv("GPIS_TRAIN_RESERVE") ? std::atoi(std::getenv("GPIS_TRAIN_RESERVE")) : 16;   // CTA slots of 296
+    const int slots = 2 * ctx->num_sms - (ctx->train_mode == 0 ? 0 : std::max(0, std::min(reserve, ctx->num_sms)));
+    const int rc = launch_leaf_train(ctx->train_stream, d_jobs, pd.njobs, (const float*)ctx->d_train_smp, ctx->tp, d_st, pd.maxN, pd.maxnb, slots,
+                                     ctx->d_k1_counter, ctx->err);
+    if (rc) return rc;
+    ctx->st.kernel_launches++;
+    CK(cudaEventRecord(ctx->ev_train[2], ctx->train_stream));
+    pd.launched = true;
+    ctx->train_ms_pending = true;
+    return 0;
+}
+static void train_read_ms(gpis_ctx* ctx, bool wait) {
+    if (!ctx->train_ms_pending) return;
+    if (!wait && cudaEventQuery(ctx->ev_train[2]) != cudaSuccess) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev_train[2]) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_train[1], ctx->ev_train[2]) == cudaSuccess)
+        ctx->st.last_train_ms = ms;
+    ctx->train_ms_pending = false;
+}
+static int train_flush(gpis_ctx* ctx) {
+    PendingTrain& pd = ctx->pend;
+    if (!pd.active) return 0;
+    NvtxRange nvtx_("K1 leaf train (wait + install)");
+    int rc = train_launch(ctx);
+    if (rc) {   // nothing ran: give the reserved records back, the leaves keep their previous GPs
+        for (auto& q : pd.plan) arena_free(ctx, q.rec, q.rb);
+        pd = PendingTrain{};
+        return rc;
+    }
+    CK(cudaEventSynchronize(ctx->ev_train[2]));
+    train_read_ms(ctx, true);
+    std::vector<SlotUpdate> ups;
+    std::vector<std::pair<uint64_t, uint64_t>> to_free;
+    for (const TrainPlan& pl : pd.plan) {
+        auto it = ctx->leaves.find(pl.key);
+        if (it == ctx->leaves.end()) { arena_free(ctx, pl.rec, pl.rb); continue; }   // cannot happen: erase flushes first
+        HostLeaf& hl = it->second;
+        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
+        hl.rec = pl.rec; hl.rec_bytes = pl.rb; hl.N = pl.N; hl.ng = pl.ng; hl.n = pl.n; hl.nb = pl.nb;
+        ups.push_back(make_update(pl.key, hl));
+        ctx->repl_touched.insert(pl.key);
+        ctx->repl_trained.insert(pl.key);
+    }
+    ctx->max_nb = std::max(ctx->max_nb, pd.maxnb);
+    ctx->max_N = std::max(ctx->max_N, pd.maxN);
+    pd = PendingTrain{};
+    rc = apply_updates(ctx, ups);
+    if (rc) return rc;
+    for (auto& f : to_free) arena_free(ctx, f.first, f.second);
+    return 0;
+}
+static void train_discard(gpis_ctx* ctx) {
+    if (ctx->train_stream) cudaStreamSynchronize(ctx->train_stream);
+    ctx->train_ms_pending = false;
+    ctx->pend = PendingTrain{};
+}
+
+int gpis_set_train_mode(gpis_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int rc = train_flush(ctx);
+    ctx->train_mode = mode;
+    return rc;
+}
+int gpis_train_wait(gpis_ctx* ctx) {
+    if (!ctx) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    return train_flush(ctx);
+}
+
 int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const float* centres,
                        const int32_t* offsets, const float* samples, int32_t* status) {
     NvtxRange nvtx_("gpis_leaves_update");
@@ -663,6 +788,7 @@ int gpis_leaves_update(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const 
     if (n_leaves == 0) return GPIS_OK;
     if (!cells || !centres || !offsets || !samples) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
 
     // ---- pass 1: validate and size every leaf; nothing is mutated yet. A leaf beyond the kernel's capacity
@@ -781,6 +907,7 @@ int gpis_samples_set(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const fl
     if (n_leaves == 0) return GPIS_OK;
     if (!cells || !centres || !offsets || (offsets[n_leaves] > 0 && !samples)) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
     for (int i = 0; i < n_leaves; ++i)
         if (offsets[i] < 0 || offsets[i + 1] < offsets[i]) { ctx->err = "offsets must be non-negative and non-decreasing"; return GPIS_ERR_ARG; }
@@ -833,10 +960,15 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     NvtxRange nvtx_("gpis_leaves_train_dirty");
     if (!ctx || n_active < 0 || !(radius > 0.f)) return GPIS_ERR_ARG;
     if (n_trained) *n_trained = 0;
-    ctx->st.last_train_leaves = 0; ctx->st.last_train_ms = 0.f; ctx->st.last_train_skipped = 0;
+    CK(cudaSetDevice(ctx->cfg.device));
+    {   // the previous batch (asynchronous modes) completes first: its buffers and the arena are about to be reused
+        const int rcf = train_flush(ctx);
+        if (rcf) return rcf;
+    }
+    ctx->st.last_train_leaves = 0; ctx->st.last_train_skipped = 0;
+    if (ctx->train_mode == 0) ctx->st.last_train_ms = 0.f;   // asynchronous modes: the most recently COMPLETED batch
     if (n_active == 0) return GPIS_OK;
     if (!active_cells) return GPIS_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
     const int dim = ctx->cfg.dim, w9 = 2 * dim + 3;
     static const bool prof = std::getenv("GPIS_PROFILE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -879,7 +1011,7 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     CK(cudaStreamSynchronize(ctx->stream));
     tq[2] = now();
     // plan: sizes, capacity, record reservation (rolled back on failure); nothing is installed before training succeeded
-    struct Plan { uint64_t key; int N, ng, n, nb; uint64_t rec, rb; };
+    using Plan = TrainPlan;
     std::vector<Plan> plan;
     std::vector<int> plan_of(ndirty, -1);
     int skipped = 0;
@@ -898,7 +1030,7 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
         nrows += N;
     }
     if (plan.empty()) { ctx->st.last_train_skipped = skipped; return GPIS_OK; }
-    rc = ensure(ctx, &ctx->d_scratch, &ctx->scratch_bytes, (uint64_t)nrows * w9 * sizeof(float));
+    rc = ensure(ctx, &ctx->d_train_smp, &ctx->train_smp_bytes, (uint64_t)nrows * w9 * sizeof(float));
     if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
     // gather only the leaves that train: compact the dirty list to those
     std::vector<int32_t> tlist, toff;
@@ -906,7 +1038,7 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     CK(cudaMemcpyAsync(d_list, tlist.data(), sizeof(int32_t) * tlist.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_off, toff.data(), sizeof(int32_t) * toff.size(), cudaMemcpyHostToDevice, ctx->stream));
     k_ball<1><<<((int)tlist.size() + 3) / 4, 128, 0, ctx->stream>>>(d_list, (int)tlist.size(), ctx->T, ctx->qp, ctx->store, radius, nullptr, nullptr,
-                                                                    d_off, (float*)ctx->d_scratch);
+                                                                    d_off, (float*)ctx->d_train_smp);
     ctx->st.kernel_launches++;
     CK(cudaGetLastError());
     std::vector<TrainJob> jobs(plan.size());
@@ -925,35 +1057,38 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
         sumN += pl.N; sumn += pl.n;
         maxN = std::max(maxN, pl.N); maxnb = std::max(maxnb, pl.nb);
     }
-    float ms = 0.f;
-    std::vector<int32_t> st(jobs.size(), 0);
     tq[3] = now();
-    rc = train_jobs(ctx, jobs, (const float*)ctx->d_scratch, maxN, maxnb, st.data(), &ms);
-    if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
-    tq[4] = now();
-    std::vector<SlotUpdate> ups;
-    std::vector<std::pair<uint64_t, uint64_t>> to_free;
-    for (const Plan& pl : plan) {
-        HostLeaf& hl = ctx->leaves[pl.key];
-        if (hl.rec) to_free.push_back({hl.rec, hl.rec_bytes});
-        hl.rec = pl.rec; hl.rec_bytes = pl.rb; hl.N = pl.N; hl.ng = pl.ng; hl.n = pl.n; hl.nb = pl.nb;
-        ups.push_back(make_update(pl.key, hl));
-        ctx->repl_touched.insert(pl.key);
-        ctx->repl_trained.insert(pl.key);
+    {   // jobs biggest-first (one CTA per leaf, the hardware scheduler balances the tail), uploaded on the main stream
+        std::vector<int> order(jobs.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].n > jobs[b].n; });
+        std::vector<TrainJob> sorted(jobs.size());
+        for (size_t i = 0; i < order.size(); ++i) sorted[i] = jobs[order[i]];
+        const uint64_t b_jobs = align_up(sorted.size() * sizeof(TrainJob), 256);
+        const uint64_t b_st = align_up(sorted.size() * sizeof(int32_t), 256);
+        rc = ensure(ctx, &ctx->d_train_jobs, &ctx->train_jobs_bytes, b_jobs + b_st);
+        if (rc) { for (auto& q : plan) arena_free(ctx, q.rec, q.rb); return rc; }
+        CK(cudaMemcpyAsync(ctx->d_train_jobs, sorted.data(), sorted.size() * sizeof(TrainJob), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `sorted`, `tlist`, `toff` go out of scope; the gather has finished too
     }
-    ctx->max_nb = std::max(ctx->max_nb, maxnb);
-    ctx->max_N = std::max(ctx->max_N, maxN);
-    rc = apply_updates(ctx, ups);
-    if (rc) return rc;
-    for (auto& f : to_free) arena_free(ctx, f.first, f.second);
+    ctx->pend = PendingTrain{};
+    ctx->pend.active = true;
+    ctx->pend.plan = plan;
+    ctx->pend.njobs = (int)jobs.size(); ctx->pend.maxN = maxN; ctx->pend.maxnb = maxnb;
     ctx->st.last_train_leaves = (int64_t)jobs.size();
     ctx->st.last_train_sum_N = sumN; ctx->st.last_train_sum_n = sumn;
     ctx->st.last_train_flops = flops; ctx->st.last_train_bytes = bytes;
-    ctx->st.last_train_ms = ms;
     ctx->st.last_train_skipped = skipped;
     if (n_trained) *n_trained = (int32_t)jobs.size();
-    if (prof) std::fprintf(stderr, "train_dirty: mark %.2f count %.2f plan+gather-launch %.2f train(wall) %.2f [kernel %.2f] install %.2f ms, %d dirty, %zu trained\n",
-                           tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], ms, now() - tq[4], ndirty, jobs.size());
+    // mode 0: train and install before returning; 1: K1 starts now on the training stream; 2: it starts at the next
+    // gpis_reeval (the next frame's device work goes first, K1 then runs beside that frame's serial host passes).
+    // In modes 1 and 2 the records are installed by the next entry point that needs them (train_flush).
+    if (ctx->train_mode == 0) rc = train_flush(ctx);
+    else if (ctx->train_mode == 1) rc = train_launch(ctx);
+    if (rc) return rc;
+    tq[4] = now();
+    if (prof) std::fprintf(stderr, "train_dirty: mark %.2f count %.2f plan+gather %.2f train(wall) %.2f [kernel %.2f] ms, %d dirty, %zu trained\n",
+                           tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], ctx->st.last_train_ms, ndirty, jobs.size());
     if (skipped) ctx->err = "gpis_leaves_train_dirty: " + std::to_string(skipped) + " leaf/leaves exceed GPIS_MAX_SAMPLES / GPIS_MAX_N and were not retrained";
     return GPIS_OK;
 }
@@ -968,6 +1103,7 @@ int gpis_leaf_get(gpis_ctx* ctx, const int32_t* cell, int32_t* N, int32_t* ng, f
                   float* gradflag, int cap_n) {
     if (!ctx || !cell) return 0;
     if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return 0;
+    if (train_flush(ctx)) return 0;
     auto it = ctx->leaves.find(key_of(ctx, cell));
     if (it == ctx->leaves.end() || it->second.rec == 0) return 0;
     const HostLeaf& hl = it->second;
@@ -997,6 +1133,7 @@ int gpis_leaf_get(gpis_ctx* ctx, const int32_t* cell, int32_t* N, int32_t* ng, f
 // ------------------------------------------------------------------ queries
 static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, int32_t* h_chosen, int32_t* h_tie) {
     NvtxRange nvtx_("gpis_query: candidates + eval + fuse");
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // queries see every record trained so far
     const int dim = ctx->cfg.dim;
     const int64_t CH = 1 << 22;  // queries per chunk (bounds scratch: ~160 B/query)
     const int64_t chunk_cap = std::min<int64_t>(n, CH);
@@ -1419,7 +1556,8 @@ int gpis_reeval(gpis_ctx* ctx, int n, const float* samples8, const gpis_frame_pa
     CK(cudaMemcpyAsync(noise, d_noise, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(grad_noise, d_gn, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    return GPIS_OK;
+    // train mode 2: the previous frame's K1 starts here, beside this frame's serial host passes
+    return train_launch(ctx);
 }
 
 // ------------------------------------------------------------------ K5 inside the library: NCCL replication
@@ -1644,6 +1782,7 @@ int gpis_replicate(gpis_ctx* ctx, int root) {
     if (!ctx->comm) { ctx->err = "gpis_replicate before gpis_comm_init"; return GPIS_ERR_STATE; }
     if (root < 0 || root >= ctx->comm_world) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     const bool is_root = ctx->comm_rank == root;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     std::vector<ReplEntry> idx;
@@ -1699,6 +1838,7 @@ int gpis_snapshot_save(gpis_ctx* ctx, const char* path) {
     NvtxRange nvtx_("gpis_snapshot_save");
     if (!ctx || !path) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     std::FILE* f = std::fopen(path, "wb");
     if (!f) { ctx->err = std::string("cannot open ") + path; return GPIS_ERR_ARG; }
     ReplHeader hd{};
@@ -1724,6 +1864,7 @@ int gpis_snapshot_load(gpis_ctx* ctx, const char* path) {
     NvtxRange nvtx_("gpis_snapshot_load");
     if (!ctx || !path) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // an asynchronous training batch completes first
     std::FILE* f = std::fopen(path, "rb");
     if (!f) { ctx->err = std::string("cannot open ") + path; return GPIS_ERR_ARG; }
     ReplHeader hd{};
@@ -1756,6 +1897,7 @@ int gpis_snapshot_load(gpis_ctx* ctx, const char* path) {
 
 int gpis_get_stats(gpis_ctx* ctx, gpis_stats* out) {
     if (!ctx || !out) return GPIS_ERR_ARG;
+    train_read_ms(ctx, false);   // never blocks: last_train_ms is the most recently completed batch
     ctx->st.leaves = (int64_t)ctx->leaves.size();
     int64_t tr = 0;
     for (auto& kv : ctx->leaves) tr += kv.second.rec ? 1 : 0;

@@ -160,11 +160,9 @@ __device__ long long g_k1_timing[8];   // clock64 ticks of block 0 per phase: A,
 #define K1_T(i)
 #endif
 
-__global__ void __launch_bounds__(TRAIN_THREADS, 2)
-k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ samples, TrainParams P,
-             int32_t* __restrict__ status) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TrainJob job = jobs[blockIdx.x];
+// one leaf, by the whole CTA
+__device__ __forceinline__ void k1_leaf(const TrainJob& job, int job_index, const float* __restrict__ samples, const TrainParams& P,
+                                        int32_t* __restrict__ status, unsigned char* smem_raw) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rg = lane >> 2, cg = lane & 3;
     const int dim = P.dim, N = job.N, ng = job.ng, n = job.n, nb = job.nb;
@@ -641,16 +639,43 @@ k_leaf_train(const TrainJob* __restrict__ jobs, const float* __restrict__ sample
         h->key = cell_key(job.cell[0], job.cell[1], dim == 3 ? job.cell[2] : 0);
         for (int c = 0; c < 3; ++c) { h->cell[c] = job.cell[c]; h->centre[c] = job.centre[c]; h->lo[c] = job.lo[c]; h->hi[c] = job.hi[c]; }
         h->cell[3] = 0; h->centre[3] = 0.f; h->lo[3] = 0.f; h->hi[3] = 0.f;
-        if (status) status[blockIdx.x] = bad_total;
+        if (status) status[job_index] = bad_total;
+    }
+    __syncthreads();   // the next leaf of this CTA reuses the shared memory and re-initialises the mbarriers
+    if (tid == 0) { mbar_inval(&bars[0]); mbar_inval(&bars[1]); mbar_inval(&bars[2]); mbar_inval(&bars[3]); }
+}
+
+// Persistent CTAs: the first gridDim.x jobs are dealt by block index, the rest are pulled from a counter in the order
+// of the (biggest-first) job list — the dynamic balance of one CTA per job without needing every CTA slot of the GPU:
+// an overlapped launch (gpis_set_train_mode) leaves a few slots free for the small kernels of the frame in progress.
+__global__ void __launch_bounds__(TRAIN_THREADS, 2)
+k_leaf_train(const TrainJob* __restrict__ jobs, int njobs, const float* __restrict__ samples, TrainParams P,
+             int32_t* __restrict__ status, int* __restrict__ next_job) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int* s_job = reinterpret_cast<int*>(smem_raw + TrainSmem::off_bar + 32);   // behind the four mbarriers (no static shared memory:
+                                                                               // the dynamic allocation may take all 227 KB)
+    int j = blockIdx.x;
+    while (j < njobs) {
+        const TrainJob job = jobs[j];
+        k1_leaf(job, j, samples, P, status, smem_raw);
+        if (threadIdx.x == 0) *s_job = (int)gridDim.x + atomicAdd(next_job, 1);
+        __syncthreads();
+        j = *s_job;
+        __syncthreads();
     }
 }
 
-// One CTA per job; dynamic shared memory sized for the largest leaf of the batch.
+// Dynamic shared memory sized for the largest leaf of the batch; max_ctas = CTA slots to use (2 per SM minus what
+// the caller wants to keep free), d_counter = one int of device memory owned by the caller's context.
 static inline int launch_leaf_train(cudaStream_t st, const TrainJob* d_jobs, int njobs, const float* d_samples,
-                                    const TrainParams& P, int32_t* d_status, int maxN, int maxnb, std::string& err) {
+                                    const TrainParams& P, int32_t* d_status, int maxN, int maxnb, int max_ctas, int* d_counter,
+                                    std::string& err) {
     if (njobs <= 0) return 0;
-    k_leaf_train<<<njobs, TRAIN_THREADS, TrainSmem::total(maxN, maxnb), st>>>(d_jobs, d_samples, P, d_status);
-    const cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) { err = std::string("k_leaf_train counter: ") + cudaGetErrorString(e); return -2; }
+    const int grid = njobs < max_ctas ? njobs : (max_ctas > 0 ? max_ctas : 1);
+    k_leaf_train<<<grid, TRAIN_THREADS, TrainSmem::total(maxN, maxnb), st>>>(d_jobs, njobs, d_samples, P, d_status, d_counter);
+    e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("k_leaf_train: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }

@@ -66,7 +66,18 @@ struct GPisMap3::Impl {
         cfg.map_noise = setting.map_noise_param;
         cfg.cluster_half = tuning.tree_cluster_half;
         cfg.search_half = tuning.tree_cluster_half * 3.0;      // GPisMap3.cpp:811  C_leng*3.0
-        return core.ensure_ctx(cfg);
+        const bool fresh = core.ctx == nullptr;
+        if (!core.ensure_ctx(cfg)) return false;
+        if (fresh) {
+            // Leaf training overlaps the next frame's host work (include/gpis_b200.h, gpis_set_train_mode): nothing in
+            // update() reads the leaf GPs, and test() waits for them inside gpis_query. GPIS_TRAIN_MODE=0 restores the
+            // reference's timing (update() returns when every GP is trained).
+            const char* e = std::getenv("GPIS_TRAIN_MODE");
+            const int mode = e ? std::atoi(e) : (device_frame ? 2 : 1);
+            if (gpis_set_train_mode(core.ctx, mode) != GPIS_OK)
+                std::fprintf(stderr, "gpismap_b200: gpis_set_train_mode(%d) failed: %s\n", mode, gpis_last_error(core.ctx));
+        }
+        return true;
     }
 
     // f-3 + f-1 on the device (gpis_frame_eval): preprocData + regressObs + the numerics of evalPoints in one call;

@@ -114,6 +114,20 @@ int gpis_samples_set(gpis_ctx* ctx, int n_leaves, const int32_t* cells, const fl
                      const float* samples);
 int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_cells, float radius, int32_t* n_trained);
 
+/* Overlap of leaf training with the next frame's host work. The reference's update() trains inside updateGPs and returns
+ * when every GP is ready (GPisMap3.cpp:218-237); nothing before the next test() reads those GPs (reEvalPoints and
+ * evalPoints use the observation GP only). gpis_set_train_mode selects when K1 of gpis_leaves_train_dirty runs:
+ *   0 (default)  before gpis_leaves_train_dirty returns;
+ *   1            at once, on a low-priority stream; gpis_leaves_train_dirty returns after the launch;
+ *   2            at the end of the next gpis_reeval (the next frame's device work goes first, K1 then runs beside that
+ *                frame's serial host passes), or at the next entry point below, whichever comes first.
+ * In modes 1 and 2 every entry point that reads or changes records, the leaf table or the arena (gpis_query*,
+ * gpis_leaf_get, gpis_leaves_*, gpis_samples_set, gpis_replicate, gpis_snapshot_*, gpis_reset) first waits for the
+ * batch and installs its records, so results never depend on the mode. gpis_train_wait does only that.
+ * gpis_stats.last_train_ms is then the most recently COMPLETED batch (gpis_get_stats never blocks). */
+int gpis_set_train_mode(gpis_ctx* ctx, int mode);
+int gpis_train_wait(gpis_ctx* ctx);
+
 /* Register leaves that hold samples but have no GP yet (a sample inserted through root growth
  * does not activate its leaf, octree.cpp:297-301, 209-211); they still count as query
  * candidates (octree.cpp:861-893). */
