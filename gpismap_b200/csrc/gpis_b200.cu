@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -175,6 +177,12 @@ struct gpis_ctx {
     // arena
     std::vector<ArenaChunk> chunks;
     std::map<uint64_t, uint64_t> free_blocks;  // address -> size
+    std::set<std::pair<uint64_t, uint64_t>> free_by_size;   // (size, address) of the same blocks
+    // arena headroom: the next chunk is cudaMalloc'ed on a helper thread before it is needed (a 1 GiB cudaMalloc takes
+    // 5-100 ms, which used to land inside a frame's update)
+    std::thread chunk_thread;
+    unsigned char* chunk_ready = nullptr;      // written by the helper, read after join()
+    uint64_t chunk_ready_bytes = 0;
     uint64_t arena_used = 0, arena_reserved = 0;
     // params
     QueryParams qp{};
@@ -259,45 +267,80 @@ static uint64_t key_of(const gpis_ctx* ctx, const int32_t* cell) {
 }
 
 // ---- arena: first-fit free list over cudaMalloc'd chunks
+// Free blocks are indexed twice: by address (coalescing) and by size (best fit in O(log F): a frame reserves ~10^3
+// records of megabytes between thousands of kilobyte-sized sample-list holes; a first-fit scan cost 5-15 ms per frame).
+static void free_add(gpis_ctx* ctx, uint64_t addr, uint64_t size) {
+    ctx->free_blocks[addr] = size;
+    ctx->free_by_size.insert({size, addr});
+}
+static void free_del(gpis_ctx* ctx, std::map<uint64_t, uint64_t>::iterator it) {
+    ctx->free_by_size.erase({it->second, it->first});
+    ctx->free_blocks.erase(it);
+}
 static int arena_alloc(gpis_ctx* ctx, uint64_t bytes, uint64_t* out) {
     bytes = align_up(bytes, 256);
-    for (auto it = ctx->free_blocks.begin(); it != ctx->free_blocks.end(); ++it) {
-        if (it->second >= bytes) {
-            const uint64_t addr = it->first, sz = it->second;
-            ctx->free_blocks.erase(it);
-            if (sz > bytes) ctx->free_blocks[addr + bytes] = sz - bytes;
-            ctx->arena_used += bytes;
-            *out = addr;
-            return 0;
-        }
+    auto bs = ctx->free_by_size.lower_bound({bytes, 0});
+    if (bs != ctx->free_by_size.end()) {
+        const uint64_t sz = bs->first, addr = bs->second;
+        free_del(ctx, ctx->free_blocks.find(addr));
+        if (sz > bytes) free_add(ctx, addr + bytes, sz - bytes);
+        ctx->arena_used += bytes;
+        *out = addr;
+        return 0;
     }
     uint64_t csz = std::max<uint64_t>(ctx->cfg.arena_chunk_bytes, align_up(bytes, 1 << 20));
     unsigned char* base = nullptr;
-    CK(cudaMalloc(&base, csz));
+    const auto t0 = std::chrono::steady_clock::now();
+    if (ctx->chunk_thread.joinable()) ctx->chunk_thread.join();
+    if (ctx->chunk_ready && ctx->chunk_ready_bytes >= csz) {      // the chunk the helper thread prepared
+        base = ctx->chunk_ready; csz = ctx->chunk_ready_bytes;
+        ctx->chunk_ready = nullptr; ctx->chunk_ready_bytes = 0;
+    } else {
+        CK(cudaMalloc(&base, csz));
+    }
+    if (std::getenv("GPIS_PROFILE"))
+        std::fprintf(stderr, "arena: new %.2f GiB chunk in %.2f ms\n", csz / 1073741824.0,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     ctx->chunks.push_back({base, csz});
     ctx->arena_reserved += csz;
-    ctx->free_blocks[(uint64_t)base] = csz;
+    free_add(ctx, (uint64_t)base, csz);
     return arena_alloc(ctx, bytes, out);
+}
+// Called once per training batch: when less than two chunks of arena space are left, prepare the next chunk in the background.
+static void arena_prefetch(gpis_ctx* ctx) {
+    if (ctx->chunk_thread.joinable() || ctx->chunk_ready) return;
+    if (ctx->arena_reserved - ctx->arena_used >= 2 * ctx->cfg.arena_chunk_bytes) return;   // a heavy frame takes 1-2 GiB of new records
+    const uint64_t csz = ctx->cfg.arena_chunk_bytes;
+    const int dev = ctx->cfg.device;
+    ctx->chunk_thread = std::thread([ctx, csz, dev] {
+        unsigned char* p = nullptr;
+        if (cudaSetDevice(dev) == cudaSuccess && cudaMalloc(&p, csz) == cudaSuccess) { ctx->chunk_ready = p; ctx->chunk_ready_bytes = csz; }
+        else (void)cudaGetLastError();     // out of memory here is not an error: arena_alloc reports it when it really needs the space
+    });
+}
+static bool same_chunk(const gpis_ctx* ctx, uint64_t a, uint64_t b) {
+    for (auto& c : ctx->chunks) if (a >= (uint64_t)c.base && b < (uint64_t)c.base + c.size) return true;
+    return false;
 }
 static void arena_free(gpis_ctx* ctx, uint64_t addr, uint64_t bytes) {
     bytes = align_up(bytes, 256);
     ctx->arena_used -= bytes;
-    auto it = ctx->free_blocks.emplace(addr, bytes).first;
     // coalesce with the next / previous block when contiguous inside one chunk
-    auto nx = std::next(it);
-    if (nx != ctx->free_blocks.end() && it->first + it->second == nx->first) {
-        bool same = false;
-        for (auto& c : ctx->chunks) if (it->first >= (uint64_t)c.base && nx->first < (uint64_t)c.base + c.size) same = true;
-        if (same) { it->second += nx->second; ctx->free_blocks.erase(nx); }
+    auto nx = ctx->free_blocks.lower_bound(addr);
+    if (nx != ctx->free_blocks.end() && addr + bytes == nx->first && same_chunk(ctx, addr, nx->first)) {
+        bytes += nx->second;
+        auto dead = nx++;
+        free_del(ctx, dead);
     }
-    if (it != ctx->free_blocks.begin()) {
-        auto pv = std::prev(it);
-        if (pv->first + pv->second == it->first) {
-            bool same = false;
-            for (auto& c : ctx->chunks) if (pv->first >= (uint64_t)c.base && it->first < (uint64_t)c.base + c.size) same = true;
-            if (same) { pv->second += it->second; ctx->free_blocks.erase(it); }
+    if (nx != ctx->free_blocks.begin()) {
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second == addr && same_chunk(ctx, pv->first, addr)) {
+            addr = pv->first;
+            bytes += pv->second;
+            free_del(ctx, pv);
         }
     }
+    free_add(ctx, addr, bytes);
 }
 
 // ---- table storage
@@ -470,7 +513,9 @@ void gpis_destroy(gpis_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     train_discard(ctx);
+    if (ctx->chunk_thread.joinable()) ctx->chunk_thread.join();
     cudaDeviceSynchronize();
+    cudaFree(ctx->chunk_ready);
     for (auto& c : ctx->chunks) cudaFree(c.base);
     cudaFree(ctx->T.keys); cudaFree(ctx->T.vals); cudaFree(ctx->T.centre); cudaFree(ctx->T.cell);
     cudaFree(ctx->T.rec); cudaFree(ctx->T.meta); cudaFree(ctx->T.lo); cudaFree(ctx->T.hi);
@@ -503,7 +548,8 @@ int gpis_reset(gpis_ctx* ctx) {
     ctx->slot_count = 0;
     ctx->tombs = 0;
     ctx->free_blocks.clear();
-    for (auto& c : ctx->chunks) ctx->free_blocks[(uint64_t)c.base] = c.size;
+    ctx->free_by_size.clear();
+    for (auto& c : ctx->chunks) free_add(ctx, (uint64_t)c.base, c.size);
     ctx->arena_used = 0;
     CK(cudaMemsetAsync(ctx->T.keys, 0, sizeof(uint64_t) * ctx->table_cap, ctx->stream));
     CK(cudaMemsetAsync(ctx->T.cell, 0, sizeof(int4) * ctx->slot_cap, ctx->stream));
@@ -1086,6 +1132,7 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     if (ctx->train_mode == 0) rc = train_flush(ctx);
     else if (ctx->train_mode == 1) rc = train_launch(ctx);
     if (rc) return rc;
+    arena_prefetch(ctx);
     tq[4] = now();
     if (prof) std::fprintf(stderr, "train_dirty: mark %.2f count %.2f plan+gather %.2f train(wall) %.2f [kernel %.2f] ms, %d dirty, %zu trained\n",
                            tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], ctx->st.last_train_ms, ndirty, jobs.size());
