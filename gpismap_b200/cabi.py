@@ -21,7 +21,7 @@ EXPORTS = [
     "gpis_obs_train_2d", "gpis_obs_train_1d", "gpis_obs_test",
     "gpis_get_stats", "gpis_comm_unique_id", "gpis_comm_init", "gpis_replicate",
     "gpis_snapshot_save", "gpis_snapshot_load", "gpis_samples_set", "gpis_leaves_train_dirty", "gpis_frame_eval", "gpis_reeval",
-    "gpis_set_train_mode", "gpis_train_wait",
+    "gpis_set_train_mode", "gpis_train_kick", "gpis_train_wait",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
         L.gpis_snapshot_load.argtypes = [vp, C.c_char_p]
         L.gpis_set_train_mode.argtypes = [vp, C.c_int]
         L.gpis_train_wait.argtypes = [vp]
+        L.gpis_train_kick.argtypes = [vp]
         _lib = L
     return _lib
 

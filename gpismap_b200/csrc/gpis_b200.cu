@@ -17,7 +17,6 @@
 #include <cstring>
 #include <map>
 #include <set>
-#include <thread>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -178,11 +177,6 @@ struct gpis_ctx {
     std::vector<ArenaChunk> chunks;
     std::map<uint64_t, uint64_t> free_blocks;  // address -> size
     std::set<std::pair<uint64_t, uint64_t>> free_by_size;   // (size, address) of the same blocks
-    // arena headroom: the next chunk is cudaMalloc'ed on a helper thread before it is needed (a 1 GiB cudaMalloc takes
-    // 5-100 ms, which used to land inside a frame's update)
-    std::thread chunk_thread;
-    unsigned char* chunk_ready = nullptr;      // written by the helper, read after join()
-    uint64_t chunk_ready_bytes = 0;
     uint64_t arena_used = 0, arena_reserved = 0;
     // params
     QueryParams qp{};
@@ -288,14 +282,16 @@ static int arena_alloc(gpis_ctx* ctx, uint64_t bytes, uint64_t* out) {
         *out = addr;
         return 0;
     }
-    uint64_t csz = std::max<uint64_t>(ctx->cfg.arena_chunk_bytes, align_up(bytes, 1 << 20));
+    // Chunks grow geometrically (each new one as large as everything reserved so far, at most 32 GiB): cudaMalloc is
+    // cheap on an idle device (0.6 ms for 1 GiB, 3 ms for 32 GiB, scripts/probe/malloc_probe.py) but waits for the
+    // kernels in flight, so a map that grows by a 1 GiB chunk every other frame paid 5-100 ms each time.
+    const uint64_t min_csz = std::max<uint64_t>(ctx->cfg.arena_chunk_bytes, align_up(bytes, 1 << 20));
+    uint64_t csz = std::max<uint64_t>(min_csz, std::min<uint64_t>(ctx->arena_reserved, 32ull << 30));
     unsigned char* base = nullptr;
     const auto t0 = std::chrono::steady_clock::now();
-    if (ctx->chunk_thread.joinable()) ctx->chunk_thread.join();
-    if (ctx->chunk_ready && ctx->chunk_ready_bytes >= csz) {      // the chunk the helper thread prepared
-        base = ctx->chunk_ready; csz = ctx->chunk_ready_bytes;
-        ctx->chunk_ready = nullptr; ctx->chunk_ready_bytes = 0;
-    } else {
+    if (cudaMalloc(&base, csz) != cudaSuccess) {      // not that much left: take what is needed
+        (void)cudaGetLastError();
+        csz = min_csz;
         CK(cudaMalloc(&base, csz));
     }
     if (std::getenv("GPIS_PROFILE"))
@@ -305,18 +301,6 @@ static int arena_alloc(gpis_ctx* ctx, uint64_t bytes, uint64_t* out) {
     ctx->arena_reserved += csz;
     free_add(ctx, (uint64_t)base, csz);
     return arena_alloc(ctx, bytes, out);
-}
-// Called once per training batch: when less than two chunks of arena space are left, prepare the next chunk in the background.
-static void arena_prefetch(gpis_ctx* ctx) {
-    if (ctx->chunk_thread.joinable() || ctx->chunk_ready) return;
-    if (ctx->arena_reserved - ctx->arena_used >= 2 * ctx->cfg.arena_chunk_bytes) return;   // a heavy frame takes 1-2 GiB of new records
-    const uint64_t csz = ctx->cfg.arena_chunk_bytes;
-    const int dev = ctx->cfg.device;
-    ctx->chunk_thread = std::thread([ctx, csz, dev] {
-        unsigned char* p = nullptr;
-        if (cudaSetDevice(dev) == cudaSuccess && cudaMalloc(&p, csz) == cudaSuccess) { ctx->chunk_ready = p; ctx->chunk_ready_bytes = csz; }
-        else (void)cudaGetLastError();     // out of memory here is not an error: arena_alloc reports it when it really needs the space
-    });
 }
 static bool same_chunk(const gpis_ctx* ctx, uint64_t a, uint64_t b) {
     for (auto& c : ctx->chunks) if (a >= (uint64_t)c.base && b < (uint64_t)c.base + c.size) return true;
@@ -513,9 +497,7 @@ void gpis_destroy(gpis_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     train_discard(ctx);
-    if (ctx->chunk_thread.joinable()) ctx->chunk_thread.join();
     cudaDeviceSynchronize();
-    cudaFree(ctx->chunk_ready);
     for (auto& c : ctx->chunks) cudaFree(c.base);
     cudaFree(ctx->T.keys); cudaFree(ctx->T.vals); cudaFree(ctx->T.centre); cudaFree(ctx->T.cell);
     cudaFree(ctx->T.rec); cudaFree(ctx->T.meta); cudaFree(ctx->T.lo); cudaFree(ctx->T.hi);
@@ -757,7 +739,7 @@ static int train_launch(gpis_ctx* ctx) {
     CK(cudaEventRecord(ctx->ev_train[1], ctx->train_stream));
     // overlapped launches keep a few CTA slots free: the on-demand observation tests of the frame in progress (a handful
     // of points each) must not wait for a leaf to finish
-    static const int reserve = std::getenv("GPIS_TRAIN_RESERVE") ? std::atoi(std::getenv("GPIS_TRAIN_RESERVE")) : 16;   // CTA slots of 296
+    static const int reserve = std::getenv("GPIS_TRAIN_RESERVE") ? std::atoi(std::getenv("GPIS_TRAIN_RESERVE")) : 32;   // CTA slots of 296
     const int slots = 2 * ctx->num_sms - (ctx->train_mode == 0 ? 0 : std::max(0, std::min(reserve, ctx->num_sms)));
     const int rc = launch_leaf_train(ctx->train_stream, d_jobs, pd.njobs, (const float*)ctx->d_train_smp, ctx->tp, d_st, pd.maxN, pd.maxnb, slots,
                                      ctx->d_k1_counter, ctx->err);
@@ -815,11 +797,16 @@ static void train_discard(gpis_ctx* ctx) {
 }
 
 int gpis_set_train_mode(gpis_ctx* ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 2) return GPIS_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 3) return GPIS_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     const int rc = train_flush(ctx);
     ctx->train_mode = mode;
     return rc;
+}
+int gpis_train_kick(gpis_ctx* ctx) {
+    if (!ctx) return GPIS_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    return train_launch(ctx);
 }
 int gpis_train_wait(gpis_ctx* ctx) {
     if (!ctx) return GPIS_ERR_ARG;
@@ -1132,7 +1119,6 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
     if (ctx->train_mode == 0) rc = train_flush(ctx);
     else if (ctx->train_mode == 1) rc = train_launch(ctx);
     if (rc) return rc;
-    arena_prefetch(ctx);
     tq[4] = now();
     if (prof) std::fprintf(stderr, "train_dirty: mark %.2f count %.2f plan+gather %.2f train(wall) %.2f [kernel %.2f] ms, %d dirty, %zu trained\n",
                            tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], ctx->st.last_train_ms, ndirty, jobs.size());
@@ -1604,7 +1590,7 @@ int gpis_reeval(gpis_ctx* ctx, int n, const float* samples8, const gpis_frame_pa
     CK(cudaMemcpyAsync(grad_noise, d_gn, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     // train mode 2: the previous frame's K1 starts here, beside this frame's serial host passes
-    return train_launch(ctx);
+    return ctx->train_mode == 2 ? train_launch(ctx) : GPIS_OK;
 }
 
 // ------------------------------------------------------------------ K5 inside the library: NCCL replication

@@ -74,6 +74,7 @@ struct GPisMap3::Impl {
             // reference's timing (update() returns when every GP is trained).
             const char* e = std::getenv("GPIS_TRAIN_MODE");
             const int mode = e ? std::atoi(e) : (device_frame ? 2 : 1);
+            train_mode = mode;
             if (gpis_set_train_mode(core.ctx, mode) != GPIS_OK)
                 std::fprintf(stderr, "gpismap_b200: gpis_set_train_mode(%d) failed: %s\n", mode, gpis_last_error(core.ctx));
         }
@@ -82,6 +83,7 @@ struct GPisMap3::Impl {
 
     // f-3 + f-1 on the device (gpis_frame_eval): preprocData + regressObs + the numerics of evalPoints in one call;
     // GPIS_HOST_FRAME=1 keeps the host implementation of those steps (identical results)
+    int train_mode = 0;
     bool device_frame = std::getenv("GPIS_HOST_FRAME") == nullptr || std::atoi(std::getenv("GPIS_HOST_FRAME")) == 0;
     std::vector<int32_t> pre_status;
     std::vector<float> pre_grad, pre_noise, pre_gnoise;
@@ -110,6 +112,7 @@ struct GPisMap3::Impl {
     ReOut reeval_compute(const ReEval& e, const float* rinv0, const float* var) const;
     void reeval_commit(const ReEval& e, const ReOut& o);
     std::vector<int> scratch_freed, scratch_touched;   // reeval_commit runs once per in-view sample
+    std::vector<int> pre_index_buf;
     void reeval_apply(const ReEval& e, const float* rinv0, const float* var);
 };
 
@@ -493,7 +496,16 @@ void GPisMap3::Impl::updateMapPoints() {
     std::vector<ReEval> st;
     std::vector<float> rinv0, var;
     std::vector<ReOut> pre_out;
-    std::vector<int> pre_index(tree->num_samples(), -1), pre_probe;
+    // sample id -> index into the pre-computed batch; a member that only ever grows, its entries are set for the
+    // in-view samples and cleared again at the end of this call (sample ids are never reused, so the array would
+    // otherwise be re-created at 4 bytes per sample EVER inserted, every frame)
+    std::vector<int>& pre_index = pre_index_buf;
+    if (pre_index.size() < tree->num_samples()) pre_index.resize(tree->num_samples() + tree->num_samples() / 4, -1);
+    std::vector<int> pre_probe;
+    struct ClearMarks {
+        std::vector<int>& idx; const std::vector<int>& ids;
+        ~ClearMarks() { for (int s : ids) idx[s] = -1; }
+    } clear_marks{pre_index, ids_all};
     if (device_frame) {
         // projection, both observation batches and the numerics of every in-view sample on the device (gpis_reeval)
         const int n = (int)ids_all.size();
@@ -768,6 +780,7 @@ void GPisMap3::update(float* dataz, int N, std::vector<float>& pose) {
         if (!reg) return;
     }
     d->updateMapPoints();                      // Step 2
+    if (d->train_mode == 3) gpis_train_kick(d->core.ctx);   // no device work of this frame until the sample lists go up
     double t3 = now_s();
     T.phase[2] = t3 - t2;
     d->core.ensure_tree();                     // Step 3 (addNewMeas, GPisMap3.cpp:571-578)

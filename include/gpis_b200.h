@@ -120,12 +120,15 @@ int gpis_leaves_train_dirty(gpis_ctx* ctx, int n_active, const int32_t* active_c
  *   0 (default)  before gpis_leaves_train_dirty returns;
  *   1            at once, on a low-priority stream; gpis_leaves_train_dirty returns after the launch;
  *   2            at the end of the next gpis_reeval (the next frame's device work goes first, K1 then runs beside that
- *                frame's serial host passes), or at the next entry point below, whichever comes first.
+ *                frame's serial host passes), or at the next entry point below, whichever comes first;
+ *   3            when gpis_train_kick is called (the host picks the point of its frame from which it has no more device
+ *                work of its own), or at the next entry point below.
  * In modes 1 and 2 every entry point that reads or changes records, the leaf table or the arena (gpis_query*,
  * gpis_leaf_get, gpis_leaves_*, gpis_samples_set, gpis_replicate, gpis_snapshot_*, gpis_reset) first waits for the
  * batch and installs its records, so results never depend on the mode. gpis_train_wait does only that.
  * gpis_stats.last_train_ms is then the most recently COMPLETED batch (gpis_get_stats never blocks). */
 int gpis_set_train_mode(gpis_ctx* ctx, int mode);
+int gpis_train_kick(gpis_ctx* ctx);
 int gpis_train_wait(gpis_ctx* ctx);
 
 /* Register leaves that hold samples but have no GP yet (a sample inserted through root growth

@@ -164,8 +164,9 @@ int gpis_leaves_train_dirty(gpis_ctx* c, int n_active, const int32_t* active, fl
     if (n_trained) *n_trained = (int32_t)c->st.last_train_leaves;
     return GPIS_OK;
 }
-int gpis_set_train_mode(gpis_ctx* c, int mode) { return (c && mode >= 0 && mode <= 2) ? GPIS_OK : GPIS_ERR_ARG; }   // the CPU stand-in always trains at once
+int gpis_set_train_mode(gpis_ctx* c, int mode) { return (c && mode >= 0 && mode <= 3) ? GPIS_OK : GPIS_ERR_ARG; }   // the CPU stand-in always trains at once
 int gpis_train_wait(gpis_ctx* c) { return c ? GPIS_OK : GPIS_ERR_ARG; }
+int gpis_train_kick(gpis_ctx* c) { return c ? GPIS_OK : GPIS_ERR_ARG; }
 int gpis_leaves_mark(gpis_ctx* c, int n, const int32_t* cells, const float* centres) {
     const int dim = c->cfg.dim;
     for (int i = 0; i < n; ++i) {

@@ -389,12 +389,12 @@ def test_gpismap3_synthetic_frames(cabi, oracle):
 
 
 def test_train_modes_give_identical_maps(cabi, monkeypatch):
-    """Overlapped leaf training (gpis_set_train_mode 1 and 2, include/gpis_b200.h) never changes a result: the samples
+    """Overlapped leaf training (gpis_set_train_mode 1, 2 and 3, include/gpis_b200.h) never changes a result: the samples
     after four frames and the answers to the same queries are bit-identical to the synchronous mode, queries issued
     right after update() see the batch that is still in flight, and the training time is reported once it completed."""
     from gpismap_b200 import hostapi, synth
     out = {}
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         monkeypatch.setenv("GPIS_TRAIN_MODE", str(mode))
         m = hostapi.GPisMap3()
         mids = []
@@ -411,7 +411,7 @@ def test_train_modes_give_identical_maps(cabi, monkeypatch):
         ph, cnt, ms = m.timing()
         out[mode] = (S, mids, rows, cnt[2])
         m.close()
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         assert np.array_equal(out[mode][0], out[0][0]), mode
         assert np.array_equal(out[mode][1], out[0][1], equal_nan=True), mode
         assert np.array_equal(out[mode][2], out[0][2], equal_nan=True), mode
