@@ -288,6 +288,13 @@ static int arena_alloc(gpis_ctx* ctx, uint64_t bytes, uint64_t* out) {
     const uint64_t min_csz = std::max<uint64_t>(ctx->cfg.arena_chunk_bytes, align_up(bytes, 1 << 20));
     uint64_t csz = std::max<uint64_t>(min_csz, std::min<uint64_t>(ctx->arena_reserved, 32ull << 30));
     unsigned char* base = nullptr;
+    static const bool prof_sync = std::getenv("GPIS_PROFILE") != nullptr;
+    double sync_ms = 0.;
+    if (prof_sync) {
+        const auto ts = std::chrono::steady_clock::now();
+        cudaDeviceSynchronize();
+        sync_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts).count();
+    }
     const auto t0 = std::chrono::steady_clock::now();
     if (cudaMalloc(&base, csz) != cudaSuccess) {      // not that much left: take what is needed
         (void)cudaGetLastError();
@@ -295,8 +302,8 @@ static int arena_alloc(gpis_ctx* ctx, uint64_t bytes, uint64_t* out) {
         CK(cudaMalloc(&base, csz));
     }
     if (std::getenv("GPIS_PROFILE"))
-        std::fprintf(stderr, "arena: new %.2f GiB chunk in %.2f ms\n", csz / 1073741824.0,
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        std::fprintf(stderr, "arena: new %.2f GiB chunk in %.2f ms (device sync before it: %.2f ms)\n", csz / 1073741824.0,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), sync_ms);
     ctx->chunks.push_back({base, csz});
     ctx->arena_reserved += csz;
     free_add(ctx, (uint64_t)base, csz);

@@ -73,7 +73,7 @@ struct GPisMap3::Impl {
             // update() reads the leaf GPs, and test() waits for them inside gpis_query. GPIS_TRAIN_MODE=0 restores the
             // reference's timing (update() returns when every GP is trained).
             const char* e = std::getenv("GPIS_TRAIN_MODE");
-            const int mode = e ? std::atoi(e) : (device_frame ? 2 : 1);
+            const int mode = e ? std::atoi(e) : (device_frame ? 3 : 1);
             train_mode = mode;
             if (gpis_set_train_mode(core.ctx, mode) != GPIS_OK)
                 std::fprintf(stderr, "gpismap_b200: gpis_set_train_mode(%d) failed: %s\n", mode, gpis_last_error(core.ctx));
@@ -110,9 +110,13 @@ struct GPisMap3::Impl {
     void reeval_stage2(std::vector<ReEval>& st, std::vector<float>& rinv0, std::vector<float>& var);
     struct ReOut { int action; float pos_new[3], grad_new[3], noise, grad_noise; };   // 0 nothing, 1 double the sigmas, 2 replace
     ReOut reeval_compute(const ReEval& e, const float* rinv0, const float* var) const;
-    void reeval_commit(const ReEval& e, const ReOut& o);
+    int reeval_commit(const ReEval& e, const ReOut& o);   // id of the fused sample it inserted, -1 if none
     std::vector<int> scratch_freed, scratch_touched;   // reeval_commit runs once per in-view sample
     std::vector<int> pre_index_buf;
+    // second-generation re-evaluations computed ahead of the serial pass (updateMapPoints)
+    std::vector<int> spec_of_pre;      // first-batch index -> index into spec_*, -1 = none
+    std::vector<ReEval> spec_st;
+    std::vector<ReOut> spec_out;
     void reeval_apply(const ReEval& e, const float* rinv0, const float* var);
 };
 
@@ -422,15 +426,15 @@ GPisMap3::Impl::ReOut GPisMap3::Impl::reeval_compute(const ReEval& e, const floa
     return out;
 }
 
-void GPisMap3::Impl::reeval_commit(const ReEval& e, const ReOut& o) {
+int GPisMap3::Impl::reeval_commit(const ReEval& e, const ReOut& o) {
     auto* tree = core.tree;
-    if (o.action == 0) return;
+    if (o.action == 0) return -1;
     if (o.action == 1) {
         Sample<3>& old = tree->sample(e.sample);
         old.pose_sig = (float)(2.0 * (double)old.pose_sig);
         old.grad_sig = (float)(2.0 * (double)old.grad_sig);
         tree->touch(e.sample);
-        return;
+        return -1;
     }
     const float noise = o.noise, grad_noise = o.grad_noise;
     const float* pos_new = o.pos_new;
@@ -440,14 +444,15 @@ void GPisMap3::Impl::reeval_commit(const ReEval& e, const ReOut& o) {
     freed.clear();
     tree->remove_tracked(e.sample, freed);
     core.drop_freed(freed);
-    if ((double)noise > 1.0 && (double)grad_noise > 0.61) return;
+    if ((double)noise > 1.0 && (double)grad_noise > 0.61) return -1;
     std::vector<int>& touched = scratch_touched;
     const int s = core.try_insert(pos_new, touched);
-    if (s < 0) return;
+    if (s < 0) return -1;
     Sample<3>& sm = tree->sample(s);
     sm.val = -setting.fbias; sm.pose_sig = noise; sm.grad_sig = grad_noise;
     sm.grad[0] = grad_new[0]; sm.grad[1] = grad_new[1]; sm.grad[2] = grad_new[2];
     core.activate(touched);
+    return s;
 }
 
 void GPisMap3::Impl::reeval_apply(const ReEval& e, const float* rinv0, const float* var) {
@@ -543,6 +548,48 @@ void GPisMap3::Impl::updateMapPoints() {
             for (int a = 0; a < 3; ++a) { o.pos_new[a] = pos_new[3 * (size_t)i + a]; o.grad_new[a] = grad_new[3 * (size_t)i + a]; }
             o.noise = noise[i]; o.grad_noise = gnoise[i];
         }
+        // Second generation. A fused sample that lands in a leaf the serial pass below has not reached yet is
+        // re-evaluated when that leaf comes up (the reference walks the tree as it is by then). Its re-evaluation is
+        // a function of its own fields and the frame only, and those fields are known now: the fused samples whose
+        // cluster-level cell changes are sent through gpis_reeval once more, in one batch, instead of a few tiny
+        // observation-test calls in the middle of the serial pass (which also land beside K1 of the previous frame).
+        {
+            const double pitch = 2.0 * (double)core.tparam.cluster_half;
+            std::vector<int> src;
+            for (int i = 0; i < n; ++i) {
+                if (act[i] != 2 || ((double)noise[i] > 1.0 && (double)gnoise[i] > 0.61)) continue;
+                bool moved = false;
+                for (int a = 0; a < 3; ++a)
+                    moved = moved || std::floor((double)smp8[8 * (size_t)i + a] / pitch) != std::floor((double)pos_new[3 * (size_t)i + a] / pitch);
+                if (moved) src.push_back(i);
+            }
+            const int n2 = (int)src.size();
+            spec_of_pre.assign(n, -1);
+            spec_st.assign(n2, ReEval{});
+            spec_out.assign(n2, ReOut{});
+            if (n2 > 0) {
+                std::vector<float> s8(8 * (size_t)n2), p2(3 * (size_t)n2), g2(3 * (size_t)n2), no2(n2), gn2(n2);
+                std::vector<int32_t> a2(n2, -1);
+                for (int j = 0; j < n2; ++j) {
+                    const int i = src[j];
+                    float* o = &s8[8 * (size_t)j];
+                    for (int a = 0; a < 3; ++a) { o[a] = pos_new[3 * (size_t)i + a]; o[3 + a] = grad_new[3 * (size_t)i + a]; }
+                    o[6] = noise[i]; o[7] = gnoise[i];
+                }
+                ProfScope ps(0);
+                if (gpis_reeval(core.ctx, n2, s8.data(), &fp, setting.map_noise_param, a2.data(), p2.data(), g2.data(), no2.data(), gn2.data()) == GPIS_OK) {
+                    for (int j = 0; j < n2; ++j) {
+                        spec_of_pre[src[j]] = j;
+                        spec_st[j].alive1 = a2[j] >= 0;
+                        ReOut& o = spec_out[j];
+                        o.action = a2[j] > 0 ? a2[j] : 0;
+                        for (int a = 0; a < 3; ++a) { o.pos_new[a] = p2[3 * (size_t)j + a]; o.grad_new[a] = g2[3 * (size_t)j + a]; }
+                        o.noise = no2[j]; o.grad_noise = gn2[j];
+                    }
+                }   // on failure nothing is speculated: the serial pass evaluates on demand
+            }
+        }
+        if (train_mode == 3) gpis_train_kick(core.ctx);   // this frame's batched device work is done: K1 of the previous frame may start
         g_prof_s[2] += now_s() - tp0; g_prof_n[2] += 1;
     } else {
     reeval_stage1(ids_all, st);
@@ -577,19 +624,34 @@ void GPisMap3::Impl::updateMapPoints() {
     std::vector<int> ids, fresh;
     std::vector<ReEval> st2;
     std::vector<float> rinv0b, varb;
+    const int base_id = (int)tree->num_samples();          // samples created below get ids from here on
+    std::vector<int> spec_of_new;                           // (id - base_id) -> index into spec_*, -1 = none
+    auto spec_of = [&](int s) { return (s >= base_id && (size_t)(s - base_id) < spec_of_new.size()) ? spec_of_new[s - base_id] : -1; };
+    const bool have_spec = device_frame && !spec_of_pre.empty();
     for (const LeafHandle& h : inview) {
         if (!tree->cell_alive(h.cell, h.gen)) continue;   // freed by a collapse; dangling pointer in the reference
         ids.clear();
         tree->collect_samples(h.cell, ids);
         fresh.clear();
-        for (int s : ids) if (s >= (int)pre_index.size() || pre_index[s] < 0) fresh.push_back(s);
+        for (int s : ids) if ((s >= (int)pre_index.size() || pre_index[s] < 0) && spec_of(s) < 0) fresh.push_back(s);
         st2.clear(); rinv0b.clear(); varb.clear();
         if (!fresh.empty()) { reeval_stage1(fresh, st2); reeval_stage2(st2, rinv0b, varb); }
         size_t fi = 0; int fprobe = 0;
         for (int s : ids) {
             if (s < (int)pre_index.size() && pre_index[s] >= 0) {
                 const int i = pre_index[s];
-                if (st[i].alive1) reeval_commit(st[i], pre_out[i]);
+                if (!st[i].alive1) continue;
+                const int ns = reeval_commit(st[i], pre_out[i]);
+                if (have_spec && ns >= 0 && spec_of_pre[i] >= 0) {      // remember what is already known about the new sample
+                    if ((size_t)(ns - base_id) >= spec_of_new.size()) spec_of_new.resize((size_t)(ns - base_id) + 64, -1);
+                    spec_of_new[ns - base_id] = spec_of_pre[i];
+                }
+            } else if (spec_of(s) >= 0) {
+                const int j = spec_of(s);
+                if (!spec_st[j].alive1) continue;
+                ReEval e = spec_st[j];
+                e.sample = s;
+                reeval_commit(e, spec_out[j]);
             } else {
                 const ReEval& e = st2[fi++];
                 if (e.alive1) { reeval_apply(e, &rinv0b[fprobe], &varb[fprobe]); fprobe += 6; }
@@ -780,7 +842,6 @@ void GPisMap3::update(float* dataz, int N, std::vector<float>& pose) {
         if (!reg) return;
     }
     d->updateMapPoints();                      // Step 2
-    if (d->train_mode == 3) gpis_train_kick(d->core.ctx);   // no device work of this frame until the sample lists go up
     double t3 = now_s();
     T.phase[2] = t3 - t2;
     d->core.ensure_tree();                     // Step 3 (addNewMeas, GPisMap3.cpp:571-578)

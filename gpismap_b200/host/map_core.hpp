@@ -183,25 +183,53 @@ public:
         {
             std::sort(sample_log.begin(), sample_log.end());
             sample_log.erase(std::unique(sample_log.begin(), sample_log.end()), sample_log.end());
+            // the changed leaves' sample lists are independent read-only walks of the tree: a few host threads, each
+            // with its own part of the (sorted) log, concatenated in log order
+            struct Part { std::vector<int32_t> cells, counts; std::vector<float> centres, samples; };
+            const int nthr = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 8, (int)sample_log.size() / 64 + 1}));
+            std::vector<Part> parts(nthr);
+            auto gather = [&](int t) {
+                Part& P = parts[t];
+                const size_t b = sample_log.size() * t / nthr, e2 = sample_log.size() * (t + 1) / nthr;
+                std::vector<int> ids;
+                for (size_t i = b; i < e2; ++i) {
+                    const auto& e = sample_log[i];
+                    if (!tree->cell_alive(e.first, e.second)) continue;      // collapsed: sync_table erased it
+                    const auto& n = tree->cell(e.first);
+                    int32_t cc[3];
+                    cell_of(e.first, cc);
+                    ids.clear();
+                    tree->collect_samples(e.first, ids);
+                    if (ids.empty() && !device_cells.count(pack(cc))) continue;
+                    for (int a = 0; a < D; ++a) { P.cells.push_back(cc[a]); P.centres.push_back(n.c[a]); }
+                    for (int s : ids) {
+                        const Sample<D>& sm = tree->sample(s);
+                        for (int a = 0; a < D; ++a) P.samples.push_back(sm.pos[a]);
+                        for (int a = 0; a < D; ++a) P.samples.push_back(sm.grad[a]);
+                        P.samples.push_back(sm.val); P.samples.push_back(sm.pose_sig); P.samples.push_back(sm.grad_sig);
+                    }
+                    P.counts.push_back((int32_t)ids.size());
+                }
+            };
+            if (nthr == 1) gather(0);
+            else {
+                std::vector<std::thread> th;
+                for (int t = 1; t < nthr; ++t) th.emplace_back(gather, t);
+                gather(0);
+                for (auto& x : th) x.join();
+            }
             std::vector<int32_t> cells, offsets(1, 0);
             std::vector<float> centres, samples;
-            std::vector<int> ids;
-            for (auto& e : sample_log) {
-                if (!tree->cell_alive(e.first, e.second)) continue;      // collapsed: sync_table erased it
-                const auto& n = tree->cell(e.first);
-                int32_t cc[3];
-                cell_of(e.first, cc);
-                ids.clear();
-                tree->collect_samples(e.first, ids);
-                if (ids.empty() && !device_cells.count(pack(cc))) continue;
-                for (int a = 0; a < D; ++a) { cells.push_back(cc[a]); centres.push_back(n.c[a]); }
-                for (int s : ids) {
-                    const Sample<D>& sm = tree->sample(s);
-                    for (int a = 0; a < D; ++a) samples.push_back(sm.pos[a]);
-                    for (int a = 0; a < D; ++a) samples.push_back(sm.grad[a]);
-                    samples.push_back(sm.val); samples.push_back(sm.pose_sig); samples.push_back(sm.grad_sig);
-                }
-                offsets.push_back((int32_t)(samples.size() / W));
+            {
+                size_t nc = 0, ns = 0;
+                for (const Part& P : parts) { nc += P.cells.size(); ns += P.samples.size(); }
+                cells.reserve(nc); centres.reserve(nc); samples.reserve(ns);
+            }
+            for (const Part& P : parts) {
+                cells.insert(cells.end(), P.cells.begin(), P.cells.end());
+                centres.insert(centres.end(), P.centres.begin(), P.centres.end());
+                samples.insert(samples.end(), P.samples.begin(), P.samples.end());
+                for (int32_t c : P.counts) offsets.push_back(offsets.back() + c);
             }
             sample_log.clear();
             const int nl = (int)offsets.size() - 1;
