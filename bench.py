@@ -390,7 +390,7 @@ def main():
                     "update_ms_per_frame_median": float(np.median(update_ms)) if update_ms else None,
                     "update_ms_per_frame_p90": float(np.percentile(update_ms, 90)) if update_ms else None,
                     "update_ms_per_frame_mean_incl_final_train_wait": float((np.sum(update_ms) + final_wait_ms) / len(update_ms)) if update_ms else None,
-                    "train_mode": int(os.environ.get("GPIS_TRAIN_MODE", "2")),
+                    "train_mode": int(os.environ.get("GPIS_TRAIN_MODE", "3")),
                     "train_kernel_ms_per_frame_median": float(np.median(train_ms)) if train_ms else None},
         }
         if world == 1 and not args.no_cpu_baseline:

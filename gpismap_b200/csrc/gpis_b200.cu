@@ -159,6 +159,8 @@ struct gpis_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // asynchronous leaf training (gpis_set_train_mode)
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};        // gpis_query with pinned host buffers: H2D | D2H beside the evaluation
+    cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t train_stream = nullptr;
     cudaEvent_t ev_train[3] = {nullptr, nullptr, nullptr};   // inputs ready (main stream) | K1 start | K1 done (training stream)
     int train_mode = 0;                                      // 0 synchronous, 1 launch at once, 2 launch at the next gpis_reeval
@@ -484,6 +486,8 @@ int gpis_create(gpis_ctx** out, const gpis_config* cfg) {
         CK(cudaStreamCreateWithPriority(&ctx->train_stream, cudaStreamNonBlocking, lo_prio));
         for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&ctx->ev_train[i]));
         CK(cudaMalloc(&ctx->d_k1_counter, 256));
+        for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
     }
     derive_params(ctx);
     uint32_t cap = 4096;
@@ -518,6 +522,8 @@ void gpis_destroy(gpis_ctx* ctx) {
     cudaFree(ctx->d_train_smp); cudaFree(ctx->d_train_jobs); cudaFree(ctx->d_k1_counter);
     for (int i = 0; i < 3; ++i) if (ctx->ev_train[i]) cudaEventDestroy(ctx->ev_train[i]);
     if (ctx->train_stream) cudaStreamDestroy(ctx->train_stream);
+    for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
+    for (int i = 0; i < 4; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     if (ctx->comm && ctx->p_ncclCommDestroy) ctx->p_ncclCommDestroy(ctx->comm);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1171,7 +1177,10 @@ int gpis_leaf_get(gpis_ctx* ctx, const int32_t* cell, int32_t* N, int32_t* ng, f
 }
 
 // ------------------------------------------------------------------ queries
-static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, int32_t* h_chosen, int32_t* h_tie) {
+// h_x / h_res (optional, pinned host memory): the caller's buffers. The chunks of x and res then travel on two copy
+// streams beside the evaluation of the neighbouring chunks (H2D of chunk c+1 and D2H of chunk c-1 overlap chunk c).
+static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, int32_t* h_chosen, int32_t* h_tie,
+                      const float* h_x = nullptr, float* h_res = nullptr) {
     NvtxRange nvtx_("gpis_query: candidates + eval + fuse");
     { const int rcf_ = train_flush(ctx); if (rcf_) return rcf_; }   // queries see every record trained so far
     const int dim = ctx->cfg.dim;
@@ -1197,11 +1206,26 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
     if (!ctx->d_acc) CK(cudaMalloc(&ctx->d_acc, sizeof(double) * 4));
     CK(cudaMemsetAsync(ctx->d_acc, 0, sizeof(double) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    for (int64_t q0 = 0; q0 < n; q0 += CH) {
+    const bool staged = h_x != nullptr && h_res != nullptr;
+    const int w2 = 2 * (1 + dim);
+    auto upload = [&](int64_t q0, int slot) -> int {
+        const int64_t nq = std::min<int64_t>(CH, n - q0);
+        CK(cudaMemcpyAsync(const_cast<float*>(d_x) + q0 * dim, h_x + q0 * dim, sizeof(float) * dim * nq, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+        CK(cudaMemcpyAsync(d_res + q0 * w2, h_res + q0 * w2, sizeof(float) * w2 * nq, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+        CK(cudaEventRecord(ctx->ev_copy[slot], ctx->copy_stream[0]));
+        return 0;
+    };
+    if (staged) { const int rcu = upload(0, 0); if (rcu) return rcu; }
+    int64_t chunk_index = 0;
+    for (int64_t q0 = 0; q0 < n; q0 += CH, ++chunk_index) {
         const int64_t nq = std::min<int64_t>(CH, n - q0);
         const float* xq = d_x + q0 * dim;
         float* rq = d_res + q0 * 2 * (1 + dim);
         const int gq = (int)((nq + 255) / 256);
+        if (staged) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[chunk_index & 1], 0));
+            if (q0 + CH < n) { const int rcu = upload(q0 + CH, (int)((chunk_index + 1) & 1)); if (rcu) return rcu; }
+        }
         CK(cudaMemsetAsync(W.counters, 0, sizeof(int32_t) * 16, ctx->stream));
         k_candidates<<<gq, 256, 0, ctx->stream>>>(xq, nq, rq, ctx->T, ctx->qp, W);
         k_candidates_exact<<<(int)((nq + 127) / 128), 128, 0, ctx->stream>>>(xq, nq, ctx->T, ctx->qp, W);
@@ -1238,9 +1262,15 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
         if (h_chosen) CK(cudaMemcpyAsync(h_chosen + q0 * 4, W.cand, sizeof(int4) * nq, cudaMemcpyDeviceToHost, ctx->stream));
         if (h_tie) CK(cudaMemcpyAsync(h_tie + q0, W.tie, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
         if (h_chosen || h_tie) CK(cudaStreamSynchronize(ctx->stream));
+        if (staged) {   // this chunk's results go home while the next chunk is evaluated
+            CK(cudaEventRecord(ctx->ev_copy[2 + (chunk_index & 1)], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream[1], ctx->ev_copy[2 + (chunk_index & 1)], 0));
+            CK(cudaMemcpyAsync(h_res + q0 * w2, rq, sizeof(float) * w2 * nq, cudaMemcpyDeviceToHost, ctx->copy_stream[1]));
+        }
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (staged) CK(cudaStreamSynchronize(ctx->copy_stream[1]));
     CK(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[1]));
     ctx->st.last_query_n = n;
     ctx->st.last_query_evals = evals;
@@ -1276,6 +1306,14 @@ static int query_host(gpis_ctx* ctx, const float* x, int64_t n, float* res, int3
         CK(cudaMalloc(&ctx->d_res, sizeof(float) * w2 * n));
         ctx->q_cap = n;
     }
+    // pinned (or registered) caller buffers: copies chunk by chunk beside the evaluation; pageable memory: cudaMemcpyAsync
+    // would block the host thread inside the chunk loop, so everything goes up first and comes back at the end
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    if (pinned(x) && pinned(res)) return query_core(ctx, (const float*)ctx->d_x, n, (float*)ctx->d_res, chosen, tie, x, res);
     CK(cudaMemcpyAsync(ctx->d_x, x, sizeof(float) * dim * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_res, res, sizeof(float) * w2 * n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = query_core(ctx, (const float*)ctx->d_x, n, (float*)ctx->d_res, chosen, tie);
