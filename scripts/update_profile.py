@@ -18,7 +18,7 @@ from gpismap_b200 import cabi
 cabi.Ctx(3, 0, borrowed=m.ctx_handle()).train_wait()   # the last batch may still be in flight (gpis_set_train_mode)
 t_all = time.perf_counter() - t_all
 print(f"sustained: {1e3 * t_all / (nf - 2):.2f} ms per frame over frames 2..{nf - 1}, back to back, incl. the final training wait "
-      f"(GPIS_TRAIN_MODE={os.environ.get('GPIS_TRAIN_MODE', 'default 2')})")
+      f"(GPIS_TRAIN_MODE={os.environ.get('GPIS_TRAIN_MODE', 'default 3')})")
 import ctypes as C
 L = hostapi.lib()
 secs = np.zeros(16); calls = np.zeros(16, np.int64)
