@@ -236,7 +236,9 @@ def main():
             update_ms.append(1e3 * (time.perf_counter() - t0))
             train_ms.append(gmap.timing()[2])
         if world > 1:
-            dist.barrier()      # replication time must not include waiting for rank 0's update
+            if rank == 0:
+                ctx.train_wait()    # the frame's K1 is still in flight (gpis_set_train_mode): replication ships trained records
+            dist.barrier()      # replication time must not include waiting for rank 0's update or training
             ctx.replicate(0)
             st_r = ctx.stats()
             repl_ms.append(st_r["last_replicate_ms"])
