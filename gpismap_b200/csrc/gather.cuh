@@ -158,6 +158,7 @@ k_ball(const int32_t* __restrict__ list, int ndirty, LeafTable T, QueryParams P,
     for (int q = 0; q < m; ++q) {
         const int ns = s_nbr[warp][q];
         const float* rows = reinterpret_cast<const float*>(S.ptr[ns]);
+        __builtin_assume(__isGlobal(rows));
         const int cnt = S.cnt[ns];
         for (int base = 0; base < cnt; base += 32) {
             const int k = base + lane;

@@ -177,8 +177,9 @@ __device__ __forceinline__ void k1_leaf(const TrainJob& job, int job_index, cons
     const int dim = P.dim, N = job.N, ng = job.ng, n = job.n, nb = job.nb;
     const int w9 = 2 * dim + 3;
 
-    float* stage[2] = {reinterpret_cast<float*>(smem_raw + TrainSmem::off_stage),
-                       reinterpret_cast<float*>(smem_raw + TrainSmem::off_stage + TrainSmem::stage_bytes)};
+    // stage(s): computed, not looked up — an array of two pointers indexed at run time loses the address space
+    float* const stage0 = reinterpret_cast<float*>(smem_raw + TrainSmem::off_stage);
+    auto stage_at = [&](int s_) { return stage0 + s_ * (TrainSmem::stage_bytes / 4); };
     float* scratch = reinterpret_cast<float*>(smem_raw + TrainSmem::off_scratch) + warp * GPIS_TILE_ELEMS;
     float* dinv_s = reinterpret_cast<float*>(smem_raw + TrainSmem::off_dinv);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TrainSmem::off_bar);
@@ -190,6 +191,15 @@ __device__ __forceinline__ void k1_leaf(const TrainJob& job, int job_index, cons
     int* wtot = reinterpret_cast<int*>(zv + nb * 32);
 
     unsigned char* rec = reinterpret_cast<unsigned char*>(job.rec);
+    // address-space hints: the record comes in as an integer and the shared-memory base as a function argument, so without
+    // them every access below is a generic LD.E / ST.E
+    __builtin_assume(__isGlobal(rec));
+    __builtin_assume(__isGlobal(samples));
+    __builtin_assume(__isShared(smem_raw));
+    __builtin_assume(__isShared(stage0));
+    __builtin_assume(__isShared(scratch)); __builtin_assume(__isShared(dinv_s));
+    __builtin_assume(__isShared(pts)); __builtin_assume(__isShared(sigx)); __builtin_assume(__isShared(sigg));
+    __builtin_assume(__isShared(yv)); __builtin_assume(__isShared(zv)); __builtin_assume(__isShared(wtot));
     float4* rec_pts = reinterpret_cast<float4*>(rec + rec_off_pts());
     float* rec_alpha = reinterpret_cast<float*>(rec + rec_off_alpha(N));
     float* rec_dinv = reinterpret_cast<float*>(rec + rec_off_dinv(N, nb));
@@ -375,9 +385,9 @@ __device__ __forceinline__ void k1_leaf(const TrainJob& job, int job_index, cons
                     ++fills[s];
                     mbar_expect_tx(&bars[s], (uint32_t)(gcount + 1) * GPIS_TILE_BYTES);
                     // A tiles of the group are consecutive in the column-block-major array
-                    tma_load_1d(stage[s], rec_tiles + (size_t)tile_index(bj + g0, bk, nb) * GPIS_TILE_ELEMS,
+                    tma_load_1d(stage_at(s), rec_tiles + (size_t)tile_index(bj + g0, bk, nb) * GPIS_TILE_ELEMS,
                                 (uint32_t)gcount * GPIS_TILE_BYTES, &bars[s]);
-                    tma_load_1d(stage[s] + TRAIN_WARPS * GPIS_TILE_ELEMS,
+                    tma_load_1d(stage_at(s) + TRAIN_WARPS * GPIS_TILE_ELEMS,
                                 rec_tiles + (size_t)tile_index(bj, bk, nb) * GPIS_TILE_ELEMS, GPIS_TILE_BYTES, &bars[s]);
                 }
             };
@@ -387,8 +397,8 @@ __device__ __forceinline__ void k1_leaf(const TrainJob& job, int job_index, cons
                 if (bk + 1 < bj) issue(bk + 1, s ^ 1);
                 mbar_wait(&bars[s], (phase_bits >> s) & 1u);
                 phase_bits ^= (1u << s);
-                const float* B = stage[s] + TRAIN_WARPS * GPIS_TILE_ELEMS;
-                if (have) tile_mma_sub(acc, stage[s] + warp * GPIS_TILE_ELEMS, B, rg, cg);
+                const float* B = stage_at(s) + TRAIN_WARPS * GPIS_TILE_ELEMS;
+                if (have) tile_mma_sub(acc, stage_at(s) + warp * GPIS_TILE_ELEMS, B, rg, cg);
                 if (rider) {
                     float sdot = 0.f;
 #pragma unroll 8
@@ -518,7 +528,7 @@ __device__ __forceinline__ void k1_leaf(const TrainJob& job, int job_index, cons
     // fp64 solution, so the CUDA path differs from the reference by the reference's error only — which is what a
     // 1e-4 contract against an fp32 reference can ask for (profiles/r02_history.md has the before/after figures).
     if (P.refine) {
-        float* rbuf = stage[1];                       // nb*32 floats: r, then u, z, d in place
+        float* rbuf = stage_at(1);                       // nb*32 floats: r, then u, z, d in place
         const float* al = zv;
         auto resid = [&](auto dimc) {
             constexpr int DIM = decltype(dimc)::value;

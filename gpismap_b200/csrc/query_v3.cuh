@@ -215,6 +215,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     const int slot = item.x, first = item.y, cnt = item.z;
     const int dim = P.dim, w = 1 + dim;
     const unsigned char* rec = reinterpret_cast<const unsigned char*>(T.rec[slot]);
+    __builtin_assume(__isGlobal(rec));   // the record address travels as an integer: without the hint its loads are generic LD.E
     const int4 meta = T.meta[slot];
     const int N = meta.x, ng = meta.y, n = meta.z, nb = meta.w;
     const int npad = nb * 32;
