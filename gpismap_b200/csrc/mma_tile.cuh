@@ -17,31 +17,39 @@ namespace gpis {
 #define E3_WAVE (E3_WARPS * E3_R)   // block rows per wave
 #define E3_STAGE_FLOATS (E3_R * 256)   // one stage: E3_R quarter tiles of 1 KB
 
-// CPL consecutive floats <-> registers: 16-byte accesses when CPL is a multiple of 4, 8-byte otherwise
+// A lane's CPL columns of a row of U <-> registers. CPL = 8 / 4: columns CPL*cg .. CPL*cg + CPL-1, one or two 16-byte
+// accesses. CPL = 6 (24-column rows): columns 4cg .. 4cg+3 and 16+2cg, 17+2cg — one 16-byte and one 8-byte access, both
+// aligned, instead of three 8-byte ones at 24-byte strides (6 instead of 7 shared-memory instructions per k-step of the
+// 16x6 lane tile). The column a register stands for only matters where results leave the tile: lane_col().
 template <int CPL>
-__device__ __forceinline__ void ld_cols(const float* __restrict__ p, float (&v)[CPL]) {
-    if constexpr (CPL % 4 == 0) {
+__device__ __forceinline__ int lane_col(int cg, int j) {
+    if constexpr (CPL == 6) return j < 4 ? 4 * cg + j : 16 + 2 * cg + (j - 4);
+    else return CPL * cg + j;
+}
+template <int CPL>
+__device__ __forceinline__ void ld_cols(const float* __restrict__ row, int cg, float (&v)[CPL]) {
+    if constexpr (CPL == 6) {
+        const float4 a = *reinterpret_cast<const float4*>(row + 4 * cg);
+        const float2 b = *reinterpret_cast<const float2*>(row + 16 + 2 * cg);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+    } else {
+        const float* p = row + CPL * cg;
 #pragma unroll
         for (int t = 0; t < CPL / 4; ++t) {
             const float4 b = *reinterpret_cast<const float4*>(p + 4 * t);
             v[4 * t] = b.x; v[4 * t + 1] = b.y; v[4 * t + 2] = b.z; v[4 * t + 3] = b.w;
         }
-    } else {
-#pragma unroll
-        for (int t = 0; t < CPL / 2; ++t) {
-            const float2 b = *reinterpret_cast<const float2*>(p + 2 * t);
-            v[2 * t] = b.x; v[2 * t + 1] = b.y;
-        }
     }
 }
 template <int CPL>
-__device__ __forceinline__ void st_cols(float* __restrict__ p, const float (&v)[CPL]) {
-    if constexpr (CPL % 4 == 0) {
+__device__ __forceinline__ void st_cols(float* __restrict__ row, int cg, const float (&v)[CPL]) {
+    if constexpr (CPL == 6) {
+        *reinterpret_cast<float4*>(row + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float2*>(row + 16 + 2 * cg) = make_float2(v[4], v[5]);
+    } else {
+        float* p = row + CPL * cg;
 #pragma unroll
         for (int t = 0; t < CPL / 4; ++t) *reinterpret_cast<float4*>(p + 4 * t) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-    } else {
-#pragma unroll
-        for (int t = 0; t < CPL / 2; ++t) *reinterpret_cast<float2*>(p + 2 * t) = make_float2(v[2 * t], v[2 * t + 1]);
     }
 }
 
@@ -54,17 +62,17 @@ __device__ __forceinline__ void qmma_sub(float (&acc)[E3_R][4][CPL], const float
     // software pipelined over k: the operands of step k+1 are loaded before the FMAs of step k are issued, so
     // the shared-memory latency is covered by this warp's own FMAs (two register operand buffers)
     const float* Ap = As + 4 * rg;
-    const float* Bp = Bq + CPL * cg;
+    const float* Bp = Bq;
     float bv[2][CPL];
     float4 av[2][R];
-    ld_cols<CPL>(Bp, bv[0]);
+    ld_cols<CPL>(Bp, cg, bv[0]);
 #pragma unroll
     for (int r = 0; r < R; ++r) av[0][r] = *reinterpret_cast<const float4*>(Ap + r * 256);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int cu = k & 1, nx = cu ^ 1;
         if (k + 1 < 8) {
-            ld_cols<CPL>(Bp + (k + 1) * NCOL, bv[nx]);
+            ld_cols<CPL>(Bp + (k + 1) * NCOL, cg, bv[nx]);
 #pragma unroll
             for (int r = 0; r < R; ++r) av[nx][r] = *reinterpret_cast<const float4*>(Ap + r * 256 + (k + 1) * 32);
         }
@@ -84,16 +92,16 @@ template <int S, int CPL, int NCOL, int KS = 8>
 __device__ __forceinline__ void qmma_one(float (&acc)[E3_R][4][CPL], const float* __restrict__ As,
                                          const float* __restrict__ Bq, int rg, int cg) {
     const float* Ap = As + S * 256 + 4 * rg;
-    const float* Bp = Bq + CPL * cg;
+    const float* Bp = Bq;
     float bv[2][CPL];
     float4 av[2];
-    ld_cols<CPL>(Bp, bv[0]);
+    ld_cols<CPL>(Bp, cg, bv[0]);
     av[0] = *reinterpret_cast<const float4*>(Ap);
 #pragma unroll 8
     for (int k = 0; k < KS; ++k) {
         const int cu = k & 1, nx = cu ^ 1;
         if (k + 1 < KS) {
-            ld_cols<CPL>(Bp + (k + 1) * NCOL, bv[nx]);
+            ld_cols<CPL>(Bp + (k + 1) * NCOL, cg, bv[nx]);
             av[nx] = *reinterpret_cast<const float4*>(Ap + (k + 1) * 32);
         }
         const float a4[4] = {av[cu].x, av[cu].y, av[cu].z, av[cu].w};

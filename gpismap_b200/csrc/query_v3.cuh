@@ -421,7 +421,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                     const float* Ui = U + (size_t)row * 32 * NCOL;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ld_cols<CPL>(Ui + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
+                        ld_cols<CPL>(Ui + (4 * rg + i) * NCOL, cg, acc[r][i]);
                 }
             }
         }
@@ -550,7 +550,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
                     if (r == cur.s_lo()) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            st_cols<CPL>(Un + (4 * rg + i) * NCOL + CPL * cg, acc[r][i]);
+                            st_cols<CPL>(Un + (4 * rg + i) * NCOL, cg, acc[r][i]);
                     }
                 }
                 __syncwarp();
@@ -622,7 +622,7 @@ k_eval_v3(const float* __restrict__ x, LeafTable T, QueryParams P, QueryWork W, 
     }
     if (rg == 0) {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) red[warp * 32 + CPL * cg + c] = ss[c];
+        for (int c = 0; c < CPL; ++c) red[warp * 32 + lane_col<CPL>(cg, c)] = ss[c];
     }
     __syncthreads();
     if (warp == 0 && lane < NCOL) {
