@@ -1199,7 +1199,6 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
         ctx->work_cap = cap;
     }
     QueryWork W = ctx->W;
-    double flops = 0, bytes_g = 0;
     int64_t evals = 0;
     int64_t items[4] = {0, 0, 0, 0};
     float ms_total = 0.f, ms_eval = 0.f;
@@ -1284,7 +1283,6 @@ static int query_core(gpis_ctx* ctx, const float* d_x, int64_t n, float* d_res, 
     // compulsory bytes: every leaf record touched counts once per pass over the batch (two passes and
     // query chunks may touch a leaf again; that is real re-reading and is charged)
     ctx->st.last_query_bytes_compulsory = 44.0 * (double)n + acc[2];
-    (void)flops; (void)bytes_g;
     return GPIS_OK;
 }
 
