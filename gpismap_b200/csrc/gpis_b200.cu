@@ -262,7 +262,7 @@ static uint64_t key_of(const gpis_ctx* ctx, const int32_t* cell) {
     return cell_key(cell[0], cell[1], ctx->cfg.dim == 3 ? cell[2] : 0);
 }
 
-// ---- arena: first-fit free list over cudaMalloc'd chunks
+// ---- arena: best-fit free list over cudaMalloc'd chunks
 // Free blocks are indexed twice: by address (coalescing) and by size (best fit in O(log F): a frame reserves ~10^3
 // records of megabytes between thousands of kilobyte-sized sample-list holes; a first-fit scan cost 5-15 ms per frame).
 static void free_add(gpis_ctx* ctx, uint64_t addr, uint64_t size) {
